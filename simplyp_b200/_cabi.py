@@ -1,0 +1,229 @@
+"""ctypes binding of ``libsimplyp_b200.so`` (``include/simplyp_b200.h``).
+
+This is the stub a maintainer of the reference would add to call the CUDA path from Python (see
+``INTEGRATION.md``).  There is no CPU fallback: if the shared library is missing, or no CUDA device
+is visible, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import packing as pk
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsimplyp_b200.so")
+
+EXPORTS = [
+    "simplyp_abi_version", "simplyp_version", "simplyp_last_error", "simplyp_device_count",
+    "simplyp_default_options", "simplyp_topology_levels", "simplyp_workspace_bytes",
+    "simplyp_run_device", "simplyp_calibrate_device", "simplyp_run_host", "simplyp_calibrate_host",
+    "simplyp_release_cache", "simplyp_launch_count", "simplyp_measure_fp64_peak",
+]
+
+
+class SimplypDims(C.Structure):
+    _fields_ = [("n_members", C.c_int32), ("n_sc", C.c_int32), ("n_days", C.c_int32),
+                ("n_sc_param_sets", C.c_int32), ("n_obs_series", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class SimplypOptions(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("step_len", C.c_double),
+                ("max_steps_per_day", C.c_int32), ("dynamic_epc0", C.c_int32),
+                ("dynamic_erodibility", C.c_int32), ("run_mode_cal", C.c_int32), ("sc_qr0", C.c_int32),
+                ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class SimplypError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built by ``__graft_entry__.build()``); raise if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SimplypError("%s not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    dp, ip, lp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_void_p
+    lib.simplyp_abi_version.restype = C.c_int
+    lib.simplyp_version.restype = C.c_char_p
+    lib.simplyp_last_error.restype = C.c_char_p
+    lib.simplyp_device_count.restype = C.c_int
+    lib.simplyp_default_options.argtypes = [C.POINTER(SimplypOptions)]
+    lib.simplyp_default_options.restype = None
+    lib.simplyp_topology_levels.argtypes = [C.c_int32, ip, ip, ip]
+    lib.simplyp_topology_levels.restype = C.c_int
+    lib.simplyp_workspace_bytes.argtypes = [C.POINTER(SimplypDims), C.c_int]
+    lib.simplyp_workspace_bytes.restype = C.c_int64
+    lib.simplyp_run_device.argtypes = [C.POINTER(SimplypDims), C.POINTER(SimplypOptions), vp, vp, vp, ip, ip,
+                                       vp, vp, vp, vp]
+    lib.simplyp_run_device.restype = C.c_int
+    lib.simplyp_calibrate_device.argtypes = [C.POINTER(SimplypDims), C.POINTER(SimplypOptions), vp, vp, vp, ip, ip,
+                                             vp, vp, vp, vp, vp, vp]
+    lib.simplyp_calibrate_device.restype = C.c_int
+    lib.simplyp_run_host.argtypes = [C.c_int, C.POINTER(SimplypDims), C.POINTER(SimplypOptions), dp, dp, dp, ip, ip,
+                                     dp, lp]
+    lib.simplyp_run_host.restype = C.c_int
+    lib.simplyp_calibrate_host.argtypes = [C.c_int, C.POINTER(SimplypDims), C.POINTER(SimplypOptions), dp, dp, dp,
+                                           ip, ip, dp, ip, dp, lp]
+    lib.simplyp_calibrate_host.restype = C.c_int
+    lib.simplyp_release_cache.restype = None
+    lib.simplyp_launch_count.restype = C.c_int64
+    lib.simplyp_measure_fp64_peak.argtypes = [C.c_int, C.c_int]
+    lib.simplyp_measure_fp64_peak.restype = C.c_double
+    if lib.simplyp_abi_version() != 1:
+        raise SimplypError("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SimplypError("simplyp_b200 error %d: %s" % (rc, load().simplyp_last_error().decode()))
+
+
+def require_device():
+    lib = load()
+    if lib.simplyp_device_count() <= 0:
+        raise SimplypError("no CUDA device visible: simplyp_b200 has no CPU fallback")
+    return lib
+
+
+def default_options(**overrides):
+    opt = SimplypOptions()
+    load().simplyp_default_options(C.byref(opt))
+    for k, v in overrides.items():
+        if not hasattr(opt, k):
+            raise AttributeError(k)
+        setattr(opt, k, v)
+    return opt
+
+
+def make_dims(n_members, n_sc, n_days, n_sc_param_sets=1, n_obs_series=0, n_edges=0):
+    d = SimplypDims()
+    d.n_members, d.n_sc, d.n_days = int(n_members), int(n_sc), int(n_days)
+    d.n_sc_param_sets, d.n_obs_series = int(n_sc_param_sets), int(n_obs_series)
+    d.reserved[0] = int(n_edges)
+    return d
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _c64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+def _topology_arrays(parent_offsets, parent_ids):
+    po = np.ascontiguousarray(parent_offsets, dtype=np.int32)
+    pid = np.ascontiguousarray(parent_ids, dtype=np.int32)
+    if pid.size == 0:
+        pid = np.zeros(1, dtype=np.int32)
+    return po, pid
+
+
+def topology_levels(parent_offsets, parent_ids):
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    S = len(po) - 1
+    lv = np.zeros(max(S, 1), dtype=np.int32)
+    n = load().simplyp_topology_levels(S, _iptr(po), _iptr(pid), _iptr(lv))
+    if n < 0:
+        _check(n)
+    return n, lv[:S]
+
+
+# ------------------------------------------------------------------------------------------ host-buffer calls
+def run_host(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, device=0, want_diag=True):
+    """numpy in / numpy out through ``simplyp_run_host``.  Returns (out [M][S][D][25], diag [M][S][4])."""
+    lib = require_device()
+    forcing = _c64(forcing)
+    member_params = _c64(member_params)
+    sc_params = _c64(sc_params)
+    if sc_params.ndim == 2:
+        sc_params = sc_params[None]
+    M, D = member_params.shape[0], forcing.shape[0]
+    Msc, S = sc_params.shape[0], sc_params.shape[1]
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    dims = make_dims(M, S, D, Msc, 0, int(po[-1]))
+    out = np.empty((M, S, D, pk.NOUT), dtype=np.float64)
+    diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
+    rc = lib.simplyp_run_host(device, C.byref(dims), C.byref(opt), _dptr(forcing), _dptr(member_params),
+                              _dptr(sc_params), _iptr(po), _iptr(pid), _dptr(out),
+                              diag.ctypes.data_as(C.POINTER(C.c_int64)) if want_diag else None)
+    _check(rc)
+    return out, diag
+
+
+def calibrate_host(forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc, opt,
+                   device=0, want_diag=True):
+    """numpy in / numpy out through ``simplyp_calibrate_host``.  Returns (stats [M][V][8], diag)."""
+    lib = require_device()
+    forcing = _c64(forcing)
+    member_params = _c64(member_params)
+    sc_params = _c64(sc_params)
+    if sc_params.ndim == 2:
+        sc_params = sc_params[None]
+    obs = _c64(obs)
+    obs_desc = np.ascontiguousarray(obs_desc, dtype=np.int32)
+    M, D = member_params.shape[0], forcing.shape[0]
+    Msc, S = sc_params.shape[0], sc_params.shape[1]
+    V = obs.shape[0]
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    dims = make_dims(M, S, D, Msc, V, int(po[-1]))
+    stats = np.empty((M, V, pk.NSTAT), dtype=np.float64)
+    diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
+    rc = lib.simplyp_calibrate_host(device, C.byref(dims), C.byref(opt), _dptr(forcing), _dptr(member_params),
+                                    _dptr(sc_params), _iptr(po), _iptr(pid), _dptr(obs), _iptr(obs_desc),
+                                    _dptr(stats), diag.ctypes.data_as(C.POINTER(C.c_int64)) if want_diag else None)
+    _check(rc)
+    return stats, diag
+
+
+# ------------------------------------------------------------------------------------------ device-pointer calls
+def run_device(dims, opt, forcing_ptr, member_ptr, sc_ptr, parent_offsets, parent_ids, out_ptr, diag_ptr,
+               ws_ptr, stream_ptr):
+    """Raw device-pointer call (torch ``.data_ptr()`` integers); enqueues on ``stream_ptr``."""
+    lib = require_device()
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    _check(lib.simplyp_run_device(C.byref(dims), C.byref(opt), forcing_ptr, member_ptr, sc_ptr, _iptr(po), _iptr(pid),
+                                  out_ptr, diag_ptr, ws_ptr, stream_ptr))
+
+
+def calibrate_device(dims, opt, forcing_ptr, member_ptr, sc_ptr, parent_offsets, parent_ids, obs_ptr, desc_ptr,
+                     stats_ptr, diag_ptr, ws_ptr, stream_ptr):
+    lib = require_device()
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    _check(lib.simplyp_calibrate_device(C.byref(dims), C.byref(opt), forcing_ptr, member_ptr, sc_ptr, _iptr(po),
+                                        _iptr(pid), obs_ptr, desc_ptr, stats_ptr, diag_ptr, ws_ptr, stream_ptr))
+
+
+def workspace_bytes(dims, calibrate):
+    n = load().simplyp_workspace_bytes(C.byref(dims), 1 if calibrate else 0)
+    if n < 0:
+        _check(int(n))
+    return int(n)
+
+
+def launch_count():
+    return int(load().simplyp_launch_count())
+
+
+def measure_fp64_peak(device=0, repeats=3):
+    require_device()
+    return float(load().simplyp_measure_fp64_peak(device, repeats))

@@ -1,0 +1,426 @@
+// simplyp_core.cuh — per-(member, sub-catchment) arithmetic of the SimplyP v0-2A daily step.
+//
+// Everything here is inline __host__ __device__ code operating on named scalars / fixed-size
+// arrays with compile-time indices, so that under nvcc the whole Runge–Kutta state lives in
+// registers.  The same header is compiled for the host ONLY by tests/hostemu (a test harness
+// that lets the CPU-only test tier exercise this arithmetic); the product library
+// (simplyp_kernels.cu) has no host execution path.
+//
+// Reference map (all line numbers: Current_Release/v0-2A/simplyP/model.py):
+//   gate()            f_x                         :23-37
+//   soilp_update()    discretized_soilP           :39-56
+//   rhs()             ode_f                       :58-187
+//   setup_thread()    run_simply_p, setup part    :318-335, :349, :377-463, :469
+//   begin_day()       run_simply_p, pre-ODE part  :497-501, :549-594, :600-611, :618
+//   dp5_attempt()     replaces scipy.integrate.odeint (LSODA), :640
+//   end_day()         run_simply_p, post-ODE part :643-724
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/simplyp_b200.h"
+
+#if defined(__CUDACC__)
+#define SP_HD __host__ __device__ __forceinline__
+#else
+#define SP_HD inline
+#endif
+
+namespace simplyp {
+
+// ------------------------------------------------------------------------------------------
+// number of live ODE states and of daily accumulators (ode_f's y[0..11] split by role)
+//   live: VsA VsS Vg Vr Qr Msus TDPr PPr      (y[0..4], y[6], y[8], y[10])
+//   acc : Qr_av Msus_out TDPr_out PPr_out     (y[5], y[7], y[9], y[11]); zero at day start (:618)
+constexpr int NL = 8;
+constexpr int NA = 4;
+enum { iVsA = 0, iVsS, iVg, iVr, iQr, iMsus, iTDPr, iPPr };
+
+// Constants of the RHS that are fixed within one day.  Kept in registers.
+struct Hot {
+  double fc, inv_fcd, mu, inv_TsA, inv_TsS, inv_Tg, Qg_min, inv_Qgd;
+  double Pin, aE;        // P*(1-f_quick), alpha*PET
+  double fA, fS, beta;
+  double qin0;           // Qq + Qr_US
+  double kQ, bQ, kM;     // a_Q*86400/((1-b_Q)*L_reach), b_Q, k_M
+  double cM, MsusUS;     // sediment source coefficient, upstream sediment
+  double tA, tS, tG, t0; // TDP: coefficients of QsA, QsS, Qg and the constant source
+  double cP, PPUS;       // PP source coefficient, upstream PP
+};
+
+// Per-thread constants and the soil-P carry that are only touched at day boundaries.
+// The CUDA kernels keep one of these per thread in shared memory (25 doubles: an odd stride,
+// so that 64-bit accesses of a half-warp fall in distinct banks).
+struct Cold {
+  double f_quick, alpha;
+  double A_catch;
+  double KfMsoil;        // Kf*Msoil
+  double inv_Msoil_EPP;  // E_PP/Msoil
+  double P_inactive;
+  double pnetA, pnetNC;  // P_netInput*A_catch*100/365 for A and NC land
+  // sediment delivery: Esus_A = baseA*C_cover_A(day) with baseA = E_M*S_reach*S_Ar*(1-C_measures_A);
+  // Esus_S, Esus_IG are constant (:591-594).  Folded with the land-use fractions they multiply:
+  double m1, m2;         // cM = m1*C_A + m2            (f_Ar*baseA ; f_IG*Esus_IG + f_S*Esus_S)
+  double pp1, pp2, pp3;  // old arable*C_A, old IG, old semi-natural (x P_inactive)   (:171-173)
+  double pp4, pp5;       // newly-converted arable*C_A, newly-converted IG + SN        (:174-176)
+  double tdpA, tdpNC;    // f_A(1-f_NC_A), f_A f_NC_A + f_S f_NC_S
+  double tdp_fixed;      // TDPeff (kg/day)
+  // soil-P state carried between days (:426-446, :684-715)
+  double PlabA, TDPsA, PlabNC, TDPsNC, concA, concNC;
+  double spare;
+};
+static_assert(sizeof(Cold) == 25 * sizeof(double), "Cold must stay 25 doubles (bank-conflict-free stride)");
+
+struct Flags {
+  int nc_is_A;       // NC land takes arable hydrology inside ode_f (:113)
+  int nc_is_S;       // NC land is semi-natural (:429, :608)
+  int post_nc_is_A;  // which hydrology the post-ODE soil-P step uses (:442, :676; leaked variable)
+};
+
+// ------------------------------------------------------------------------------------------
+SP_HD double sp_max(double a, double b) { return a > b ? a : b; }
+SP_HD double sp_min(double a, double b) { return a < b ? a : b; }
+
+// f_x(x, thr, 0.01) expressed on u = (x-thr)/(thr*0.01): 0 for u<0, 1 for u>1, 3u^2-2u^3 between.
+SP_HD double gate(double u) {
+  u = sp_min(sp_max(u, 0.0), 1.0);
+  return u * u * (3.0 - 2.0 * u);
+}
+
+// ------------------------------------------------------------------------------------------
+// ode_f: derivatives of the 8 live states; the 4 accumulator derivatives come out separately.
+SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&da)[NA]) {
+  const double VsA = y[iVsA], VsS = y[iVsS], Vg = y[iVg], Vr = y[iVr], Qr = y[iQr];
+  // soil boxes (:105-110)
+  const double xA = VsA - c.fc, xS = VsS - c.fc;
+  const double QsA = xA * gate(xA * c.inv_fcd) * c.inv_TsA;
+  const double QsS = xS * gate(xS * c.inv_fcd) * c.inv_TsS;
+  dy[iVsA] = c.Pin - c.aE * (1.0 - exp(-c.mu * VsA)) - QsA;
+  dy[iVsS] = c.Pin - c.aE * (1.0 - exp(-c.mu * VsS)) - QsS;
+  // groundwater (:121-124)
+  const double xg = Vg * c.inv_Tg - c.Qg_min;
+  const double Qg = c.Qg_min + gate(xg * c.inv_Qgd) * xg;
+  const double soil = c.fA * QsA + c.fS * QsS;
+  dy[iVg] = c.beta * soil - Qg;
+  // reach (:127-132); Qr^b_Q and Qr^k_M share one logarithm
+  const double net = c.qin0 + (1.0 - c.beta) * soil + Qg - Qr;
+  const double lq = log(Qr);
+  const double qb = exp(c.bQ * lq);
+  const double qk = exp(c.kM * lq);
+  dy[iQr] = net * c.kQ * qb;
+  dy[iVr] = net;
+  da[0] = Qr;
+  // outflow rate of the reach, 1/day
+  const double r = Qr / Vr;
+  // sediment (:138-147)
+  const double oM = y[iMsus] * r;
+  dy[iMsus] = c.cM * qk + c.MsusUS - oM;
+  da[1] = oM;
+  // TDP (:154-168)
+  const double oT = y[iTDPr] * r;
+  dy[iTDPr] = c.tA * QsA + c.tS * QsS + c.tG * Qg + c.t0 - oT;
+  da[2] = oT;
+  // PP (:171-180)
+  const double oP = y[iPPr] * r;
+  dy[iPPr] = c.cP * qk + c.PPUS - oP;
+  da[3] = oP;
+}
+
+// ------------------------------------------------------------------------------------------
+// discretized_soilP (:39-56).  pnet = P_netInput*A_catch*100/365.
+SP_HD void soilp_update(double pnet, double KfMsoil, double EPC0, double Qs, double Qq, double Vs,
+                        double& TDPs, double& Plab) {
+  const double a = pnet + KfMsoil * EPC0;
+  const double b = (KfMsoil + Qs + Qq) / Vs;
+  const double ab = a / b;
+  const double e = exp(-b);
+  TDPs = ab + (TDPs - ab) * e;                                   // :44
+  double sorp = 0.0;
+  if (Vs > 0.0) {                                                // :50
+    const double ab0 = a / (b * Vs);
+    sorp = KfMsoil * (ab0 - EPC0 + (1.0 / b) * (TDPs / Vs - ab0) * (1.0 - e));   // :51 (updated TDPs)
+  }
+  Plab = Plab + sorp;                                            // :54
+}
+
+// Dynamic arable crop-cover factor (:354-361, :563-580), triangular wave around the two
+// erosion-risk mid-points; `dayNo in np.arange(start, end)` is reproduced literally.
+SP_HD double season_cover(double doy, double mid, double C_cover) {
+  const double half = 30.0;  // E_risk_period/2
+  const double start = mid - half, end = mid + half;
+  const double k = doy - start;
+  const bool inside = (k >= 0.0) && (doy < end) && (k == floor(k));
+  if (inside) {
+    if (doy < mid) return C_cover + (1.0 - C_cover) * (doy - start) / (mid - start);
+    return 1.0 + (C_cover - 1.0) * (doy - mid) / (end - mid);
+  }
+  return C_cover - (60.0 * (1.0 - C_cover) / (2.0 * (365.0 - 60.0)));
+}
+
+// ------------------------------------------------------------------------------------------
+// One-off setup of a (member, sub-catchment) thread: derived parameters and initial conditions.
+//   mp      : member parameter row [SIMPLYP_NP_MEMBER]
+//   sp      : this sub-catchment's parameter row [SIMPLYP_NP_SC]
+//   A_qr0   : A_catch of the sub-catchment p['SC_Qr0'] (:386)
+//   nc_last : NC type of the LAST sub-catchment in run order (0 none, 1 'A', 2 'S'), for the
+//             leaked-variable quirk; pass this SC's own type to disable it
+SP_HD void setup_thread(const double* mp, const double* sp, double A_qr0, int nc_last, int strict_quirks,
+                        int run_mode_cal, Hot& h, Cold& c, Flags& fl, double (&y)[NL], double& Kf_out) {
+  const double A = sp[SIMPLYP_SC_A_CATCH];
+  const double fAr = sp[SIMPLYP_SC_F_AR], fIG = sp[SIMPLYP_SC_F_IG], fS = sp[SIMPLYP_SC_F_S];
+  const double fNCAr = sp[SIMPLYP_SC_F_NC_AR], fNCIG = sp[SIMPLYP_SC_F_NC_IG], fNCS = sp[SIMPLYP_SC_F_NC_S];
+  const double fA = fIG + fAr;                                   // :318
+  const double fNCA = fAr * fNCAr + fNCIG * fIG;                 // :319
+  int nc = 0;                                                    // :325-334
+  if (fNCA > 0.0) nc = 1; else if (fNCS > 0.0) nc = 2;
+  fl.nc_is_A = (nc == 1);
+  fl.nc_is_S = (nc == 2);
+  fl.post_nc_is_A = strict_quirks ? (nc_last == 1) : (nc == 1);
+
+  const double fc = mp[SIMPLYP_P_FC];
+  h.fc = fc;
+  h.inv_fcd = 1.0 / (fc * 0.01);
+  h.mu = -log(0.01) / fc;                                        // :349
+  h.inv_TsA = 1.0 / mp[SIMPLYP_P_TS_A];
+  h.inv_TsS = 1.0 / mp[SIMPLYP_P_TS_S];
+  h.inv_Tg = 1.0 / mp[SIMPLYP_P_T_G];
+  h.Qg_min = mp[SIMPLYP_P_QG_MIN];
+  h.inv_Qgd = 1.0 / (h.Qg_min * 0.01);
+  h.fA = fA;
+  h.fS = fS;
+  h.beta = mp[SIMPLYP_P_BETA];
+  const double aQ = mp[SIMPLYP_P_A_Q], bQ = mp[SIMPLYP_P_B_Q];
+  h.kQ = aQ * 86400.0 / ((1.0 - bQ) * sp[SIMPLYP_SC_L_REACH]);   // :130
+  h.bQ = bQ;
+  h.kM = mp[SIMPLYP_P_K_M];
+  h.tG = mp[SIMPLYP_P_TDPG] * A;                                 // UC_Cinv(TDPg, A_catch), :163
+  h.Pin = h.aE = h.qin0 = h.cM = h.MsusUS = h.tA = h.tS = h.t0 = h.cP = h.PPUS = 0.0;
+
+  c.f_quick = mp[SIMPLYP_P_F_QUICK];
+  c.alpha = mp[SIMPLYP_P_ALPHA];
+  c.A_catch = A;
+  const double Msoil = mp[SIMPLYP_P_MSOIL_M2] * 1e6 * A;         // :404
+  c.P_inactive = 1e-6 * mp[SIMPLYP_P_SOILP_S] * Msoil;           // :407
+  const double EPC0_0_A = mp[SIMPLYP_P_EPC0_A] * A;              // :412
+  const double EPC0_0_S = mp[SIMPLYP_P_EPC0_S] * A;
+  const double Plab0_A = 1e-6 * (mp[SIMPLYP_P_SOILP_A] - mp[SIMPLYP_P_SOILP_S]) * Msoil;   // :415
+  const double TDPs0_A = EPC0_0_A * fc;                          // :420 (VsA0 = fc)
+  double Kf;
+  if (run_mode_cal) Kf = 1e-6 * (mp[SIMPLYP_P_SOILP_A] - mp[SIMPLYP_P_SOILP_S]) / EPC0_0_A;   // :451
+  else Kf = mp[SIMPLYP_P_KF];
+  Kf_out = Kf;
+  c.KfMsoil = Kf * Msoil;
+  c.inv_Msoil_EPP = mp[SIMPLYP_P_E_PP] / Msoil;
+  c.pnetA = mp[SIMPLYP_P_PNET_A] * A * 100.0 / 365.0;            // :42
+  c.pnetNC = mp[SIMPLYP_P_PNET_NC] * A * 100.0 / 365.0;
+  const double EM_Sr = mp[SIMPLYP_P_E_M] * sp[SIMPLYP_SC_S_REACH];           // :591-594
+  const double baseA = EM_Sr * sp[SIMPLYP_SC_S_AR] * (1.0 - mp[SIMPLYP_P_CMEAS_A]);
+  const double eS = EM_Sr * sp[SIMPLYP_SC_S_SN] * mp[SIMPLYP_P_CCOVER_S] * (1.0 - mp[SIMPLYP_P_CMEAS_S]);
+  const double eIG = EM_Sr * sp[SIMPLYP_SC_S_IG] * mp[SIMPLYP_P_CCOVER_IG] * (1.0 - mp[SIMPLYP_P_CMEAS_IG]);
+  c.m1 = fAr * baseA;                                            // :141
+  c.m2 = fIG * eIG + fS * eS;                                    // :142-143
+  c.pp1 = fAr * (1.0 - fNCAr) * baseA;                           // :171
+  c.pp2 = fIG * (1.0 - fNCIG) * eIG;                             // :172
+  c.pp3 = fS * (1.0 - fNCS) * eS * c.P_inactive;                 // :173
+  c.pp4 = fAr * fNCAr * baseA;                                   // :174
+  c.pp5 = fIG * fNCIG * eIG + fS * fNCS * eS;                    // :175-176
+  c.spare = 0.0;
+  c.tdpA = fA * (1.0 - fNCA);                                    // :155,159
+  c.tdpNC = fA * fNCA + fS * fNCS;                               // :156-157,160-161
+  double TDPeff = sp[SIMPLYP_SC_TDPEFF];
+  if (TDPeff != TDPeff) TDPeff = 0.0;                            // blank cell -> 0, :462-463
+  c.tdp_fixed = TDPeff;
+
+  // soil-P carry (:426-446)
+  c.PlabA = Plab0_A;
+  c.TDPsA = TDPs0_A;
+  if (nc == 2) { c.PlabNC = Plab0_A; c.TDPsNC = TDPs0_A; }       // :429-431
+  else { c.PlabNC = 0.0; c.TDPsNC = 0.0; }                       // :433-434 (TDPs0['S'] = 0)
+  c.concA = TDPs0_A / fc;                                        // :438
+  c.concNC = c.TDPsNC / fc;                                      // :446 (VsA0 == VsS0 == fc)
+  (void)EPC0_0_S;
+
+  // hydrology initial conditions (:377-390, :457-459)
+  const double Qr0 = mp[SIMPLYP_P_QR0_INIT] * 86400.0 / (1000.0 * A_qr0);    // UC_Qinv, :386
+  y[iVsA] = fc;
+  y[iVsS] = fc;
+  y[iVg] = mp[SIMPLYP_P_BETA] * Qr0 * mp[SIMPLYP_P_T_G];
+  y[iQr] = Qr0;
+  y[iVr] = sp[SIMPLYP_SC_L_REACH] / (aQ * pow(Qr0, bQ) * 86400.0) * Qr0;
+  y[iMsus] = 0.0;
+  y[iTDPr] = 0.0;
+  y[iPPr] = 0.0;
+}
+
+// Values of a day that end up in the output row but are not states.
+struct DayAux {
+  double Qq, C_cover_A, EPC0_A, EPC0_NC;
+};
+
+// Pre-ODE part of one day (:497-501, :549-611): fills the day-dependent members of Hot.
+//   P, E, doy : forcing of the day;  us[4] : upstream Qr (already area-scaled), Msus, TDP, PP
+SP_HD void begin_day(const double* mp, const double* sp, const Cold& c, const Flags& fl,
+                     int dynamic_epc0, int dynamic_erod, double P, double E, double doy,
+                     const double (&us)[4], Hot& h, DayAux& aux) {
+  const double Qq = c.f_quick * P;                               // :501
+  aux.Qq = Qq;
+  h.Pin = P * (1.0 - c.f_quick);
+  h.aE = c.alpha * E;
+  h.qin0 = Qq + us[0];
+  h.MsusUS = us[1];
+  h.PPUS = us[3];
+  // erodibility (:549-594)
+  double CA = mp[SIMPLYP_P_CCOVER_A];
+  if (dynamic_erod) {
+    const double f_spr = sp[SIMPLYP_SC_F_SPR];
+    CA = f_spr * season_cover(doy, mp[SIMPLYP_P_D_MAXE_SPR], CA)
+         + (1.0 - f_spr) * season_cover(doy, mp[SIMPLYP_P_D_MAXE_AUT], CA);   // :579-580
+  }
+  aux.C_cover_A = CA;
+  h.cM = c.m1 * CA + c.m2;                                       // :141-143
+  // EPC0 (:600-611)
+  double EPC0_A, EPC0_NC;
+  if (dynamic_epc0) {
+    EPC0_A = sp_max(c.PlabA / c.KfMsoil, 0.0);
+    EPC0_NC = sp_max(c.PlabNC / c.KfMsoil, 0.0);
+  } else {
+    EPC0_A = mp[SIMPLYP_P_EPC0_A] * c.A_catch;
+    EPC0_NC = fl.nc_is_S ? EPC0_A : mp[SIMPLYP_P_EPC0_S] * c.A_catch;
+  }
+  aux.EPC0_A = EPC0_A;
+  aux.EPC0_NC = EPC0_NC;
+  // TDP source coefficients with today's soil-water concentrations (:154-166)
+  const double cTA = c.tdpA * c.concA;
+  const double cTNC = c.tdpNC * c.concNC;
+  const double omb = 1.0 - h.beta;
+  if (fl.nc_is_A) { h.tA = omb * (cTA + cTNC); h.tS = 0.0; }
+  else            { h.tA = omb * cTA;          h.tS = omb * cTNC; }
+  h.t0 = (cTA + cTNC) * Qq + c.tdp_fixed + us[2];
+  // PP source coefficient with today's labile P (:171-176)
+  const double pA = c.PlabA + c.P_inactive, pN = c.PlabNC + c.P_inactive;
+  h.cP = c.inv_Msoil_EPP * ((c.pp1 * CA + c.pp2) * pA + c.pp3 + (c.pp4 * CA + c.pp5) * pN);
+}
+
+// Post-ODE part of one day (:648-715).  Applies the groundwater floor to y, advances the soil-P
+// carry in `c`, and fills the 13 non-ODE output values.
+SP_HD void end_day(const Hot& h, Cold& c, const Flags& fl, int dynamic_epc0, const DayAux& aux,
+                   double (&y)[NL], double (&non)[13]) {
+  const double xA = y[iVsA] - h.fc, xS = y[iVsS] - h.fc;
+  const double QsA = xA * gate(xA * h.inv_fcd) * h.inv_TsA;      // :663-664
+  const double QsS = xS * gate(xS * h.inv_fcd) * h.inv_TsS;
+  const double xg = y[iVg] * h.inv_Tg - h.Qg_min;                // :668-670
+  const double Qg = h.Qg_min + gate(xg * h.inv_Qgd) * xg;
+  y[iVg] = Qg / h.inv_Tg;
+  const double VsNC = fl.post_nc_is_A ? y[iVsA] : y[iVsS];       // :676-681
+  const double QsNC = fl.post_nc_is_A ? QsA : QsS;
+  if (dynamic_epc0) {                                            // :684-703
+    soilp_update(c.pnetA, c.KfMsoil, aux.EPC0_A, QsA, aux.Qq, y[iVsA], c.TDPsA, c.PlabA);
+    soilp_update(c.pnetNC, c.KfMsoil, aux.EPC0_NC, QsNC, aux.Qq, VsNC, c.TDPsNC, c.PlabNC);
+    c.TDPsA = sp_max(c.TDPsA, 0.0);
+    c.PlabA = sp_max(c.PlabA, 0.0);
+    c.TDPsNC = sp_max(c.TDPsNC, 0.0);
+    c.PlabNC = sp_max(c.PlabNC, 0.0);
+    c.concA = c.TDPsA / y[iVsA];
+    c.concNC = c.TDPsNC / VsNC;
+  } else {                                                       // :707-715
+    c.concA = aux.EPC0_A;
+    c.concNC = aux.EPC0_NC;
+  }
+  non[0] = aux.Qq;  non[1] = QsA;  non[2] = QsS;  non[3] = Qg;  non[4] = aux.C_cover_A;
+  non[5] = aux.EPC0_A;  non[6] = aux.EPC0_NC;
+  non[7] = c.TDPsA;  non[8] = c.PlabA;  non[9] = c.concA;
+  non[10] = c.TDPsNC;  non[11] = c.PlabNC;  non[12] = c.concNC;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dormand–Prince 5(4) with FSAL.  The accumulators are pure quadratures (the RHS does not depend
+// on them), so their stage derivatives are folded into two running sums (5th-order weights and
+// error weights) instead of being stored per stage.
+struct RK {
+  double k1[NL];   // derivative at the current (t, y): reused after a rejection, FSAL after acceptance
+  double a1[NA];   // accumulator derivatives at the current point
+};
+
+namespace dp {
+constexpr double a21 = 1.0 / 5.0;
+constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0, a54 = -212.0 / 729.0;
+constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0, a64 = 49.0 / 176.0,
+                 a65 = -5103.0 / 18656.0;
+constexpr double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
+                 e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+}  // namespace dp
+
+// One step attempt of size hh from (y, acc).  On return ynew/accnew hold the 5th-order solution,
+// k7/a7 the derivative there, and the return value is the scaled RMS error (<= 1 accepts);
+// a non-finite error is returned as +inf.
+SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc)[NA], const RK& rk, double hh,
+                         double rtol, double atol, double (&ynew)[NL], double (&accnew)[NA], double (&k7)[NL],
+                         double (&a7)[NA]) {
+  using namespace dp;
+  double k2[NL], k3[NL], k4[NL], k5[NL], k6[NL], yt[NL], da[NA];
+  double sb[NA], se[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] = b1 * rk.a1[i]; se[i] = e1 * rk.a1[i]; }
+
+#pragma unroll
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a21 * rk.k1[i]);
+  rhs(c, yt, k2, da);  // b2 = e2 = 0: no accumulator contribution
+#pragma unroll
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a31 * rk.k1[i] + a32 * k2[i]);
+  rhs(c, yt, k3, da);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] += b3 * da[i]; se[i] += e3 * da[i]; }
+#pragma unroll
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a41 * rk.k1[i] + a42 * k2[i] + a43 * k3[i]);
+  rhs(c, yt, k4, da);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] += b4 * da[i]; se[i] += e4 * da[i]; }
+#pragma unroll
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a51 * rk.k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+  rhs(c, yt, k5, da);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] += b5 * da[i]; se[i] += e5 * da[i]; }
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+    yt[i] = y[i] + hh * (a61 * rk.k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+  rhs(c, yt, k6, da);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] += b6 * da[i]; se[i] += e6 * da[i]; }
+#pragma unroll
+  for (int i = 0; i < NL; ++i)
+    ynew[i] = y[i] + hh * (b1 * rk.k1[i] + b3 * k3[i] + b4 * k4[i] + b5 * k5[i] + b6 * k6[i]);
+  rhs(c, ynew, k7, a7);
+
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const double err = hh * (e1 * rk.k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k7[i]);
+    const double sc = atol + rtol * sp_max(fabs(y[i]), fabs(ynew[i]));
+    const double q = err / sc;
+    s += q * q;
+  }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    accnew[i] = acc[i] + hh * sb[i];
+    const double err = hh * (se[i] + e7 * a7[i]);
+    const double sc = atol + rtol * sp_max(fabs(acc[i]), fabs(accnew[i]));
+    const double q = err / sc;
+    s += q * q;
+  }
+  const double en = sqrt(s * (1.0 / (NL + NA)));
+  return (en == en) ? en : INFINITY;   // NaN -> reject
+}
+
+// Step-size factor of the elementary controller for a 5(4) pair: 0.9*err^(-1/5) in [0.2, 5].
+SP_HD double step_factor(double en) {
+  if (!(en > 1e-30)) return 5.0;
+  if (!(en < 1e30)) return 0.2;
+  const double f = 0.9 * exp(-0.2 * log(en));
+  return sp_min(5.0, sp_max(0.2, f));
+}
+
+}  // namespace simplyp

@@ -1,0 +1,674 @@
+// simplyp_kernels.cu — sm_100a kernels and the C-ABI of simplyp_b200 (see include/simplyp_b200.h).
+//
+// Kernels
+//   simplyp_integrate_kernel<CAL>   K1 (+K1b routing, K2 output writer or K3 fused statistics):
+//                                   one thread per (ensemble member, sub-catchment); replaces the
+//                                   reference's SC x day loop body, model.py:365-724
+//   obs_const_kernel                observation-only constants of the fit statistics
+//                                   (visualise_results.py:441-449 denominators)
+//   fp64_peak_kernel                DFMA throughput probe for the roofline denominator
+//
+// There is deliberately no host implementation of the integration in this library.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "simplyp_thread.cuh"
+
+using namespace simplyp;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ errors
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+#define SP_CUDA(call)                                                            \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #call, cudaGetErrorString(e__)); \
+      return (e__ == cudaErrorMemoryAllocation) ? SIMPLYP_ENOMEM : SIMPLYP_ECUDA; \
+    }                                                                            \
+  } while (0)
+
+__device__ int g_zero_offsets[2] = {0, 0};   // CSR offsets of a network without edges
+
+// ------------------------------------------------------------------------------------------ kernel args
+struct KArgs {
+  int M, S, D, Msc, V;
+  ThreadOptions topt;
+  int sc_qr0;
+  const double* forcing;        // [D][4]
+  const double* member_params;  // [M][NP_MEMBER]
+  const double* sc_params;      // [Msc][S][NP_SC]
+  const int* parent_offsets;    // [S+1]   (device copy)
+  const int* parent_ids;        // [E]
+  const int* work_sc;           // sub-catchments handled by this launch
+  int n_work;
+  double* out;                  // run: [M][S][D][25]
+  long long* diag;              // [M][S][4] or null
+  const double* obs;            // cal: [V][D]
+  const int* obs_desc;          // cal: [V][2]
+  const double* obs_const;      // cal: [V][8]
+  double* stats;                // cal: [M][V][8]
+  double* flux;                 // cal, S>1: [M][S][D][4]
+};
+
+// raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
+enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
+// obs_const[V][8]
+enum { OC_N = 0, OC_MEAN, OC_SS, OC_MEAN_LOG, OC_SS_LOG, OC_SUM, OC_STD };
+
+// ------------------------------------------------------------------------------------------ IO policies
+struct IOBase {
+  const KArgs& a;
+  int m, s;
+  const double* scp_member;  // this member's [S][NP_SC] block
+  __device__ IOBase(const KArgs& a_, int m_, int s_)
+      : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC) {}
+
+  __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy) const {
+    const double2 f = __ldg(reinterpret_cast<const double2*>(a.forcing + (size_t)day * SIMPLYP_NF));
+    P = f.x;
+    E = f.y;
+    doy = __ldg(a.forcing + (size_t)day * SIMPLYP_NF + 2);
+  }
+};
+
+// Full-output mode: parents' fluxes are read back from their output rows (columns Qr, Msus_kg/day,
+// TDP_kg/day, PP_kg/day — exactly what the reference reads from df_R_dict, model.py:524-528).
+struct RunIO : IOBase {
+  using IOBase::IOBase;
+  __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
+    us[0] = us[1] = us[2] = us[3] = 0.0;
+    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
+    if (e0 == e1) return;
+    const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    for (int e = e0; e < e1; ++e) {
+      const int p = a.parent_ids[e];
+      const double* row = a.out + (((size_t)m * a.S + p) * a.D + day) * SIMPLYP_NOUT;
+      const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+      us[0] += __ldcg(row + SIMPLYP_O_QR) * (A_up / A_this);   // :525
+      us[1] += __ldcg(row + SIMPLYP_O_MSUS_FLUX);
+      us[2] += __ldcg(row + SIMPLYP_O_TDP_FLUX);
+      us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
+    }
+  }
+  __device__ __forceinline__ void emit(int day, const double (&y)[NL], const double (&acc)[NA],
+                                       const double (&non)[13], const Cold&) const {
+    double* row = a.out + (((size_t)m * a.S + s) * a.D + day) * SIMPLYP_NOUT;
+    row[SIMPLYP_O_VSA] = y[iVsA];
+    row[SIMPLYP_O_VSS] = y[iVsS];
+    row[SIMPLYP_O_VG] = y[iVg];
+    row[SIMPLYP_O_VR] = y[iVr];
+    row[SIMPLYP_O_QR_END] = y[iQr];
+    row[SIMPLYP_O_QR] = acc[0];
+    row[SIMPLYP_O_MSUS_END] = y[iMsus];
+    row[SIMPLYP_O_MSUS_FLUX] = acc[1];
+    row[SIMPLYP_O_TDPR_END] = y[iTDPr];
+    row[SIMPLYP_O_TDP_FLUX] = acc[2];
+    row[SIMPLYP_O_PPR_END] = y[iPPr];
+    row[SIMPLYP_O_PP_FLUX] = acc[3];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) row[SIMPLYP_O_QQ + i] = non[i];
+  }
+};
+
+// Calibration mode: nothing is written per day except (for S>1) the 4 fluxes the downstream reach
+// needs; observed days update the running sums of the fit statistics.
+struct CalIO : IOBase {
+  double f_TDP;
+  __device__ CalIO(const KArgs& a_, int m_, int s_, double f_TDP_) : IOBase(a_, m_, s_), f_TDP(f_TDP_) {}
+
+  __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
+    us[0] = us[1] = us[2] = us[3] = 0.0;
+    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
+    if (e0 == e1) return;
+    const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    for (int e = e0; e < e1; ++e) {
+      const int p = a.parent_ids[e];
+      const double* row = a.flux + (((size_t)m * a.S + p) * a.D + day) * 4;
+      const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+      us[0] += __ldcg(row + 0) * (A_up / A_this);
+      us[1] += __ldcg(row + 1);
+      us[2] += __ldcg(row + 2);
+      us[3] += __ldcg(row + 3);
+    }
+  }
+  __device__ __forceinline__ void emit(int day, const double (&)[NL], const double (&acc)[NA],
+                                       const double (&)[13], const Cold& c) const {
+    if (a.flux != nullptr) {
+      double* row = a.flux + (((size_t)m * a.S + s) * a.D + day) * 4;
+      row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = acc[3];
+    }
+    for (int v = 0; v < a.V; ++v) {
+      if (__ldg(a.obs_desc + 2 * v) != s) continue;
+      const double o = __ldg(a.obs + (size_t)v * a.D + day);
+      if (o != o) continue;  // no observation that day
+      const int kind = __ldg(a.obs_desc + 2 * v + 1);
+      // simulated counterpart (model.py:784-793, :840-845)
+      const double A = c.A_catch;
+      const double tdp = (acc[2] / acc[0]) / A, pp = (acc[3] / acc[0]) / A;
+      double sim;
+      switch (kind) {
+        case SIMPLYP_V_Q:   sim = acc[0] * A * 1000.0 / 86400.0; break;
+        case SIMPLYP_V_SS:  sim = (acc[1] / acc[0]) / A; break;
+        case SIMPLYP_V_TDP: sim = tdp; break;
+        case SIMPLYP_V_PP:  sim = pp; break;
+        case SIMPLYP_V_TP:  sim = tdp + pp; break;
+        default:            sim = tdp * f_TDP; break;
+      }
+      const double* oc = a.obs_const + 8 * v;
+      const double mo = __ldg(oc + OC_MEAN);
+      const double em = __ldg(a.member_params + (size_t)m * SIMPLYP_NP_MEMBER + SIMPLYP_P_ERR_M0 + kind);
+      double* rs = a.stats + ((size_t)m * a.V + v) * SIMPLYP_NSTAT;
+      const double d = o - sim;
+      const double dl = log(o) - log(sim);
+      const double sg = em * sim;
+      const double ds = sim - mo;
+      rs[RS_N] += 1.0;
+      rs[RS_SSE] += d * d;
+      rs[RS_SSE_LOG] += dl * dl;
+      rs[RS_LL] += -0.91893853320467274178 - log(sg) - d * d / (2.0 * sg * sg);   // MCMC.ipynb:233-236
+      rs[RS_S1] += ds;
+      rs[RS_S2] += ds * ds;
+      rs[RS_SOS] += (o - mo) * ds;
+      rs[RS_SABS] += fabs(d);
+    }
+  }
+  // turn the raw sums of this thread's series into the statistics of visualise_results.py:441-449
+  __device__ void finalise() const {
+    for (int v = 0; v < a.V; ++v) {
+      if (a.obs_desc[2 * v] != s) continue;
+      const double* oc = a.obs_const + 8 * v;
+      double* rs = a.stats + ((size_t)m * a.V + v) * SIMPLYP_NSTAT;
+      const double n = rs[RS_N], sse = rs[RS_SSE], ssel = rs[RS_SSE_LOG], ll = rs[RS_LL];
+      const double s1 = rs[RS_S1], s2 = rs[RS_S2], sos = rs[RS_SOS], sabs = rs[RS_SABS];
+      const double ss_o = oc[OC_SS], ss_lo = oc[OC_SS_LOG], sum_o = oc[OC_SUM], std_o = oc[OC_STD];
+      const double var_s = s2 - s1 * s1 / n;
+      rs[SIMPLYP_ST_N] = n;
+      rs[SIMPLYP_ST_NSE] = 1.0 - sse / ss_o;
+      rs[SIMPLYP_ST_LOG_NSE] = 1.0 - ssel / ss_lo;
+      rs[SIMPLYP_ST_LOGLIK] = (ll == ll) ? ll : -INFINITY;       // NaN -> -inf, MCMC.ipynb:238-240
+      rs[SIMPLYP_ST_R2] = (sos * sos) / (ss_o * var_s);
+      rs[SIMPLYP_ST_PBIAS] = 100.0 * (s1 + n * oc[OC_MEAN] - sum_o) / sum_o;
+      rs[SIMPLYP_ST_NRMSD] = 100.0 * (sabs / n) / std_o;
+      rs[SIMPLYP_ST_SSE] = sse;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ K1
+template <bool CAL>
+__global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
+  extern __shared__ double smem_cold[];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.n_work * a.M) return;
+  const int w = (int)(idx / a.M);
+  const int m = (int)(idx - (long long)w * a.M);
+  const int s = a.work_sc ? a.work_sc[w] : w;
+
+  Cold& c = *reinterpret_cast<Cold*>(smem_cold + (size_t)threadIdx.x * (sizeof(Cold) / sizeof(double)));
+  const double* mp = a.member_params + (size_t)m * SIMPLYP_NP_MEMBER;
+  const double* scp = a.sc_params + (size_t)(a.Msc > 1 ? m : 0) * a.S * SIMPLYP_NP_SC;
+  const double* sp = scp + (size_t)s * SIMPLYP_NP_SC;
+  const double A_qr0 = scp[(size_t)a.sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+  // NC type of the last sub-catchment in run order (the reference's leaked loop variable)
+  const double* spl = scp + (size_t)(a.S - 1) * SIMPLYP_NP_SC;
+  const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
+  const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
+
+  ThreadCounters cnt;
+  if (CAL) {
+    CalIO io(a, m, s, mp[SIMPLYP_P_F_TDP]);
+    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
+    io.finalise();
+  } else {
+    RunIO io(a, m, s);
+    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
+  }
+  if (a.diag) {
+    long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
+    dg[SIMPLYP_DG_STEPS] = cnt.steps;
+    dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
+    dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
+    dg[SIMPLYP_DG_STATUS] = cnt.status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ obs constants
+// One block per observed series: n, mean, sum of squares about the mean (plain and log), sum, std.
+__global__ void obs_const_kernel(const double* obs, int D, double* obs_const) {
+  const int v = blockIdx.x;
+  const double* o = obs + (size_t)v * D;
+  __shared__ double red[5][256];
+  double n = 0, s = 0, sl = 0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double x = o[d];
+    if (x == x) { n += 1.0; s += x; sl += log(x); }
+  }
+  red[0][threadIdx.x] = n; red[1][threadIdx.x] = s; red[2][threadIdx.x] = sl;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) for (int j = 0; j < 3; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + k];
+    __syncthreads();
+  }
+  const double N = red[0][0], mean = red[1][0] / N, meanl = red[2][0] / N, sum = red[1][0];
+  __syncthreads();
+  double ss = 0, ssl = 0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double x = o[d];
+    if (x == x) { ss += (x - mean) * (x - mean); const double l = log(x) - meanl; ssl += l * l; }
+  }
+  red[3][threadIdx.x] = ss; red[4][threadIdx.x] = ssl;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) for (int j = 3; j < 5; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* oc = obs_const + 8 * v;
+    oc[OC_N] = N; oc[OC_MEAN] = mean; oc[OC_SS] = red[3][0]; oc[OC_MEAN_LOG] = meanl;
+    oc[OC_SS_LOG] = red[4][0]; oc[OC_SUM] = sum; oc[OC_STD] = sqrt(red[3][0] / N); oc[7] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ FP64 peak probe
+__global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == 123.456) sink[0] = r;
+}
+
+// ------------------------------------------------------------------------------------------ host helpers
+int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<int>& lvl) {
+  lvl.assign(S, 0);
+  int nl = S > 0 ? 1 : 0;
+  for (int s = 0; s < S; ++s) {
+    if (po[s + 1] < po[s]) return SIMPLYP_EINVAL;
+    int L = 0;
+    for (int e = po[s]; e < po[s + 1]; ++e) {
+      const int p = pid[e];
+      if (p < 0 || p >= s) return SIMPLYP_EINVAL;   // parents must come earlier in run order
+      L = L > lvl[p] + 1 ? L : lvl[p] + 1;
+    }
+    lvl[s] = L;
+    nl = nl > L + 1 ? nl : L + 1;
+  }
+  return nl;
+}
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t off_po, off_pid, off_order, off_oc, off_flux, total;
+};
+
+WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
+  WsLayout L;
+  size_t o = 0;
+  L.off_po = o;    o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
+  L.off_pid = o;   o = align_up(o + sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
+  L.off_order = o; o = align_up(o + sizeof(int) * (size_t)d.n_sc);
+  L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
+  L.off_flux = o;
+  if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
+  L.total = o;
+  return L;
+}
+
+int check_common(const SimplypDims* dims, const SimplypOptions* opt, const void* forcing, const void* mp,
+                 const void* scp, const int32_t* po) {
+  if (!dims || !opt || !forcing || !mp || !scp || !po) return fail(SIMPLYP_EINVAL, "null argument%s");
+  if (dims->n_members <= 0 || dims->n_sc <= 0 || dims->n_days < 0) return fail(SIMPLYP_EINVAL, "bad dims%s");
+  if (dims->n_sc_param_sets != 1 && dims->n_sc_param_sets != dims->n_members)
+    return fail(SIMPLYP_EINVAL, "n_sc_param_sets must be 1 or n_members%s");
+  if (opt->sc_qr0 < 0 || opt->sc_qr0 >= dims->n_sc) return fail(SIMPLYP_EINVAL, "sc_qr0 out of range%s");
+  if (!(opt->rtol > 0.0) || !(opt->atol >= 0.0) || !(opt->step_len > 0.0))
+    return fail(SIMPLYP_EINVAL, "rtol/atol/step_len must be positive%s");
+  return SIMPLYP_OK;
+}
+
+ThreadOptions make_topt(const SimplypOptions& o) {
+  ThreadOptions t;
+  t.rtol = o.rtol; t.atol = o.atol; t.step_len = o.step_len;
+  t.max_steps_per_day = o.max_steps_per_day > 0 ? o.max_steps_per_day : 5000;
+  t.dynamic_epc0 = o.dynamic_epc0; t.dynamic_erod = o.dynamic_erodibility;
+  t.run_mode_cal = o.run_mode_cal; t.strict_quirks = o.strict_quirks;
+  return t;
+}
+
+int pick_block(long long n_threads, int requested) {
+  if (requested > 0) return requested > 128 ? 128 : (requested < 32 ? 32 : (requested / 32) * 32);
+  // keep at least ~2 blocks per SM so every SM sub-partition gets warps at small ensemble sizes
+  if (n_threads >= 148LL * 2 * 128) return 128;
+  if (n_threads >= 148LL * 2 * 64) return 64;
+  return 32;
+}
+
+// Shared launcher: level-major sweep over the reach DAG (each launch handles the sub-catchments of
+// one topological level for all members; a level only reads fluxes written by earlier launches).
+template <bool CAL>
+int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, const int32_t* po_host,
+                  const int32_t* pid_host, char* ws, cudaStream_t st) {
+  const int S = dims.n_sc;
+  std::vector<int> lvl;
+  const int nl = topology_levels(S, po_host, pid_host, lvl);
+  if (nl < 0) return fail(SIMPLYP_EINVAL, "topology: parents must precede children in run order%s");
+  const int E = po_host[S];
+  const WsLayout L = ws_layout(dims, E, CAL);
+  std::vector<int> order;
+  order.reserve(S);
+  std::vector<int> level_start(nl + 1, 0);
+  for (int l = 0; l < nl; ++l) {
+    level_start[l] = (int)order.size();
+    for (int s = 0; s < S; ++s) if (lvl[s] == l) order.push_back(s);
+  }
+  level_start[nl] = (int)order.size();
+
+  if (S > 1 || E > 0) {
+    if (!ws) return fail(SIMPLYP_EINVAL, "workspace required for n_sc > 1%s");
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_po, po_host, sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
+    if (E > 0) SP_CUDA(cudaMemcpyAsync(ws + L.off_pid, pid_host, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_order, order.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    // the host vectors above are pageable: the copies are staged before these calls return
+    a.parent_offsets = reinterpret_cast<const int*>(ws + L.off_po);
+    a.parent_ids = reinterpret_cast<const int*>(ws + L.off_pid);
+  } else {
+    int* zp = nullptr;
+    SP_CUDA(cudaGetSymbolAddress((void**)&zp, g_zero_offsets));
+    a.parent_offsets = zp;   // {0, 0}: no parents
+    a.parent_ids = zp;
+  }
+  if (CAL) a.flux = (S > 1) ? reinterpret_cast<double*>(ws + L.off_flux) : nullptr;
+
+  for (int l = 0; l < nl; ++l) {
+    const int n_work = level_start[l + 1] - level_start[l];
+    if (n_work == 0) continue;
+    a.n_work = n_work;
+    a.work_sc = (S > 1) ? reinterpret_cast<const int*>(ws + L.off_order) + level_start[l] : nullptr;
+    const long long n_threads = (long long)n_work * dims.n_members;
+    const int block = pick_block(n_threads, opt.threads_per_block);
+    const long long grid = (n_threads + block - 1) / block;
+    const size_t smem = (size_t)block * sizeof(Cold);
+    simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    SP_CUDA(cudaGetLastError());
+  }
+  return SIMPLYP_OK;
+}
+
+KArgs base_args(const SimplypDims& dims, const SimplypOptions& opt, const double* forcing,
+                const double* member_params, const double* sc_params) {
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = dims.n_members; a.S = dims.n_sc; a.D = dims.n_days; a.Msc = dims.n_sc_param_sets;
+  a.V = dims.n_obs_series;
+  a.topt = make_topt(opt);
+  a.sc_qr0 = opt.sc_qr0;
+  a.forcing = forcing; a.member_params = member_params; a.sc_params = sc_params;
+  return a;
+}
+
+// cached device buffers of the _host entry points
+struct HostCache {
+  int device = -1;
+  void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t stream = nullptr;
+} g_cache;
+
+int cache_get(int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 8;
+  if (g_cache.cap[slot] < bytes) {
+    if (g_cache.buf[slot]) cudaFree(g_cache.buf[slot]);
+    g_cache.buf[slot] = nullptr;
+    g_cache.cap[slot] = 0;
+    SP_CUDA(cudaMalloc(&g_cache.buf[slot], bytes));
+    g_cache.cap[slot] = bytes;
+  }
+  *out = g_cache.buf[slot];
+  return SIMPLYP_OK;
+}
+
+int cache_select_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  if (device < 0 || device >= n) return fail(SIMPLYP_EINVAL, "device index out of range%s");
+  if (g_cache.device != device) {
+    simplyp_release_cache();
+    g_cache.device = device;
+  }
+  SP_CUDA(cudaSetDevice(device));
+  if (!g_cache.stream) SP_CUDA(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+  return SIMPLYP_OK;
+}
+
+}  // namespace
+
+// ============================================================================================ C-ABI
+extern "C" {
+
+int simplyp_abi_version(void) { return SIMPLYP_ABI_VERSION; }
+const char* simplyp_version(void) { return "simplyp_b200 0.1.0 (sm_100a)"; }
+const char* simplyp_last_error(void) { return g_err; }
+
+int simplyp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void simplyp_default_options(SimplypOptions* opt) {
+  if (!opt) return;
+  memset(opt, 0, sizeof(*opt));
+  opt->rtol = 1e-7;
+  opt->atol = 1e-10;
+  opt->step_len = 1.0;
+  opt->max_steps_per_day = 5000;
+  opt->run_mode_cal = 1;
+  opt->strict_quirks = 1;
+}
+
+int simplyp_topology_levels(int32_t n_sc, const int32_t* parent_offsets, const int32_t* parent_ids,
+                            int32_t* levels) {
+  if (n_sc < 0 || !parent_offsets || (!parent_ids && parent_offsets[n_sc] > 0) || !levels)
+    return fail(SIMPLYP_EINVAL, "null argument%s");
+  std::vector<int> lvl;
+  const int nl = topology_levels(n_sc, parent_offsets, parent_ids, lvl);
+  if (nl < 0) return fail(SIMPLYP_EINVAL, "topology: parents must precede children in run order%s");
+  for (int s = 0; s < n_sc; ++s) levels[s] = lvl[s];
+  return nl;
+}
+
+int64_t simplyp_workspace_bytes(const SimplypDims* dims, int calibrate) {
+  if (!dims) return SIMPLYP_EINVAL;
+  return (int64_t)ws_layout(*dims, dims->reserved[0], calibrate != 0).total;
+}
+
+int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                       const double* member_params, const double* sc_params, const int32_t* parent_offsets,
+                       const int32_t* parent_ids, double* out, int64_t* diag, void* workspace, void* stream) {
+  int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
+  if (rc) return rc;
+  if (!out) return fail(SIMPLYP_EINVAL, "null output%s");
+  if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  if (dims->n_days == 0) return SIMPLYP_OK;
+  KArgs a = base_args(*dims, *opt, forcing, member_params, sc_params);
+  a.out = out;
+  a.diag = reinterpret_cast<long long*>(diag);
+  return launch_levels<false>(*dims, *opt, a, parent_offsets, parent_ids, static_cast<char*>(workspace),
+                              static_cast<cudaStream_t>(stream));
+}
+
+int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                             const double* member_params, const double* sc_params,
+                             const int32_t* parent_offsets, const int32_t* parent_ids, const double* obs,
+                             const int32_t* obs_desc, double* stats, int64_t* diag, void* workspace,
+                             void* stream) {
+  int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
+  if (rc) return rc;
+  if (dims->n_obs_series < 0 || (dims->n_obs_series > 0 && (!obs || !obs_desc || !stats)))
+    return fail(SIMPLYP_EINVAL, "null observation/statistics argument%s");
+  if (!workspace) return fail(SIMPLYP_EINVAL, "workspace required%s");
+  if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int V = dims->n_obs_series;
+  const WsLayout L = ws_layout(*dims, parent_offsets[dims->n_sc], true);
+  char* ws = static_cast<char*>(workspace);
+  KArgs a = base_args(*dims, *opt, forcing, member_params, sc_params);
+  a.diag = reinterpret_cast<long long*>(diag);
+  a.obs = obs;
+  a.obs_desc = obs_desc;
+  a.stats = stats;
+  a.obs_const = reinterpret_cast<const double*>(ws + L.off_oc);
+  if (V > 0) {
+    SP_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * SIMPLYP_NSTAT * (size_t)dims->n_members * V, st));
+    if (dims->n_days > 0) {
+      obs_const_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, reinterpret_cast<double*>(ws + L.off_oc));
+      g_launches.fetch_add(1);
+      SP_CUDA(cudaGetLastError());
+    }
+  }
+  if (dims->n_days == 0) return SIMPLYP_OK;
+  return launch_levels<true>(*dims, *opt, a, parent_offsets, parent_ids, ws, st);
+}
+
+int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                     const double* member_params, const double* sc_params, const int32_t* parent_offsets,
+                     const int32_t* parent_ids, double* out, int64_t* diag) {
+  int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
+  if (rc) return rc;
+  if (!out) return fail(SIMPLYP_EINVAL, "null output%s");
+  rc = cache_select_device(device);
+  if (rc) return rc;
+  cudaStream_t st = g_cache.stream;
+  const size_t M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
+  const size_t b_forc = sizeof(double) * SIMPLYP_NF * D, b_mp = sizeof(double) * SIMPLYP_NP_MEMBER * M;
+  const size_t b_sc = sizeof(double) * SIMPLYP_NP_SC * Msc * S, b_out = sizeof(double) * SIMPLYP_NOUT * M * S * D;
+  const size_t b_diag = sizeof(int64_t) * SIMPLYP_NDIAG * M * S;
+  SimplypDims d2 = *dims;
+  d2.reserved[0] = parent_offsets[S];
+  const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, 0);
+  void *d_forc, *d_mp, *d_sc, *d_out, *d_diag, *d_ws;
+  if ((rc = cache_get(0, b_forc, &d_forc)) || (rc = cache_get(1, b_mp, &d_mp)) || (rc = cache_get(2, b_sc, &d_sc)) ||
+      (rc = cache_get(3, b_out, &d_out)) || (rc = cache_get(4, b_diag, &d_diag)) || (rc = cache_get(5, b_ws, &d_ws)))
+    return rc;
+  SP_CUDA(cudaMemcpyAsync(d_forc, forcing, b_forc, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_mp, member_params, b_mp, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_sc, sc_params, b_sc, cudaMemcpyHostToDevice, st));
+  rc = simplyp_run_device(dims, opt, (const double*)d_forc, (const double*)d_mp, (const double*)d_sc,
+                          parent_offsets, parent_ids, (double*)d_out, (int64_t*)d_diag, d_ws, st);
+  if (rc) return rc;
+  SP_CUDA(cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  if (diag) SP_CUDA(cudaMemcpyAsync(diag, d_diag, b_diag, cudaMemcpyDeviceToHost, st));
+  SP_CUDA(cudaStreamSynchronize(st));
+  return SIMPLYP_OK;
+}
+
+int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                           const double* member_params, const double* sc_params, const int32_t* parent_offsets,
+                           const int32_t* parent_ids, const double* obs, const int32_t* obs_desc, double* stats,
+                           int64_t* diag) {
+  int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
+  if (rc) return rc;
+  if (dims->n_obs_series <= 0 || !obs || !obs_desc || !stats)
+    return fail(SIMPLYP_EINVAL, "observations and statistics buffers required%s");
+  rc = cache_select_device(device);
+  if (rc) return rc;
+  cudaStream_t st = g_cache.stream;
+  const size_t M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
+  const size_t V = dims->n_obs_series;
+  const size_t b_forc = sizeof(double) * SIMPLYP_NF * D, b_mp = sizeof(double) * SIMPLYP_NP_MEMBER * M;
+  const size_t b_sc = sizeof(double) * SIMPLYP_NP_SC * Msc * S;
+  const size_t b_obs = sizeof(double) * V * D, b_desc = sizeof(int32_t) * 2 * V;
+  const size_t b_stats = sizeof(double) * SIMPLYP_NSTAT * M * V, b_diag = sizeof(int64_t) * SIMPLYP_NDIAG * M * S;
+  SimplypDims d2 = *dims;
+  d2.reserved[0] = parent_offsets[S];
+  const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, 1);
+  void *d_forc, *d_mp, *d_sc, *d_obs, *d_desc, *d_stats, *d_diag, *d_ws;
+  if ((rc = cache_get(0, b_forc, &d_forc)) || (rc = cache_get(1, b_mp, &d_mp)) || (rc = cache_get(2, b_sc, &d_sc)) ||
+      (rc = cache_get(3, b_stats, &d_stats)) || (rc = cache_get(4, b_diag, &d_diag)) ||
+      (rc = cache_get(5, b_ws, &d_ws)) || (rc = cache_get(6, b_obs, &d_obs)) || (rc = cache_get(7, b_desc, &d_desc)))
+    return rc;
+  SP_CUDA(cudaMemcpyAsync(d_forc, forcing, b_forc, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_mp, member_params, b_mp, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_sc, sc_params, b_sc, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_obs, obs, b_obs, cudaMemcpyHostToDevice, st));
+  SP_CUDA(cudaMemcpyAsync(d_desc, obs_desc, b_desc, cudaMemcpyHostToDevice, st));
+  rc = simplyp_calibrate_device(dims, opt, (const double*)d_forc, (const double*)d_mp, (const double*)d_sc,
+                                parent_offsets, parent_ids, (const double*)d_obs, (const int32_t*)d_desc,
+                                (double*)d_stats, (int64_t*)d_diag, d_ws, st);
+  if (rc) return rc;
+  SP_CUDA(cudaMemcpyAsync(stats, d_stats, b_stats, cudaMemcpyDeviceToHost, st));
+  if (diag) SP_CUDA(cudaMemcpyAsync(diag, d_diag, b_diag, cudaMemcpyDeviceToHost, st));
+  SP_CUDA(cudaStreamSynchronize(st));
+  return SIMPLYP_OK;
+}
+
+void simplyp_release_cache(void) {
+  for (int i = 0; i < 8; ++i) {
+    if (g_cache.buf[i]) cudaFree(g_cache.buf[i]);
+    g_cache.buf[i] = nullptr;
+    g_cache.cap[i] = 0;
+  }
+  if (g_cache.stream) cudaStreamDestroy(g_cache.stream);
+  g_cache.stream = nullptr;
+  g_cache.device = -1;
+}
+
+int64_t simplyp_launch_count(void) { return g_launches.load(); }
+
+double simplyp_measure_fp64_peak(int device, int repeats) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+    return -1.0;
+  }
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  double* sink = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  fp64_peak_kernel<<<blocks, threads>>>(sink, 64, 0.999999, 1e-9);   // warm-up
+  cudaDeviceSynchronize();
+  double best = 0.0;
+  for (int r = 0; r < (repeats > 0 ? repeats : 3); ++r) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(sink, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  g_launches.fetch_add(1 + (repeats > 0 ? repeats : 3));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return best;
+}
+
+}  // extern "C"

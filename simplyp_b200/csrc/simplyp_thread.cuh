@@ -1,0 +1,125 @@
+// simplyp_thread.cuh — the program one (member, sub-catchment) work item executes over all days.
+//
+// Control flow: ONE flattened loop whose iteration is a single Dormand–Prince step attempt.  A
+// thread that completes a day runs the day-boundary code (post-ODE algebra, output/statistics,
+// next day's pre-ODE algebra) inside the same loop and carries on, so the lanes of a warp never
+// wait for each other at day boundaries: they only re-converge on the step body, which is where
+// >95 % of the instructions are.  This replaces the reference's "for day: odeint(...)" nest
+// (model.py:491-724).
+//
+// The IO policy supplies forcing, upstream fluxes and the output sink, so the same program serves
+// the full-output kernel, the calibration kernel and the host-side test harness.
+#pragma once
+
+#include "simplyp_core.cuh"
+
+namespace simplyp {
+
+struct ThreadOptions {
+  double rtol, atol, step_len;
+  int max_steps_per_day;
+  int dynamic_epc0, dynamic_erod, run_mode_cal, strict_quirks;
+};
+
+struct ThreadCounters {
+  long long steps, rejected, rhs_evals;
+  int status;
+};
+
+// IO policy concept:
+//   void forcing(int day, double& P, double& E, double& doy);
+//   void upstream(int day, double (&us)[4]);     // area-scaled Qr, Msus, TDP, PP of the parents, summed
+//   void emit(int day, const double (&y)[NL], const double (&acc)[NA], const double (&non)[13],
+//             const Cold& c);                    // y holds the raw end-of-day ODE states
+template <class IO>
+SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int nc_last,
+                         const ThreadOptions& opt, int n_days, Cold& c, IO& io, ThreadCounters& cnt) {
+  Hot h;
+  Flags fl;
+  RK rk;
+  DayAux aux;
+  double y[NL], acc[NA], us[4];
+  double Kf;
+  setup_thread(mp, sp, A_qr0, nc_last, opt.strict_quirks, opt.run_mode_cal, h, c, fl, y, Kf);
+  cnt.steps = cnt.rejected = cnt.rhs_evals = 0;
+  cnt.status = 0;
+  if (n_days <= 0) return;
+
+  int day = 0;
+  double P, E, doy;
+  io.forcing(day, P, E, doy);
+  io.upstream(day, us);
+  begin_day(mp, sp, c, fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+  rhs(h, y, rk.k1, rk.a1);
+  cnt.rhs_evals = 1;
+
+  const double T = opt.step_len;
+  double t = 0.0;
+  double hstep = 0.05 * T;   // first guess; the controller takes over after the first attempt
+  int day_steps = 0;
+  bool grow_ok = true;
+
+  while (true) {
+    const double rem = T - t;
+    const bool last = hstep * 1.0000001 >= rem;
+    const double hh = last ? rem : hstep;
+
+    double ynew[NL], accnew[NA], k7[NL], a7[NA];
+    const double en = dp5_attempt(h, y, acc, rk, hh, opt.rtol, opt.atol, ynew, accnew, k7, a7);
+    cnt.steps += 1;
+    cnt.rhs_evals += 6;
+    day_steps += 1;
+
+    bool accept = en <= 1.0;
+    if (!accept && day_steps >= opt.max_steps_per_day) {   // give up on error control for this day
+      accept = true;
+      cnt.status |= 1;
+    }
+    double fac = step_factor(en);
+    if (accept) {
+      t += hh;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) { y[i] = ynew[i]; rk.k1[i] = k7[i]; }
+#pragma unroll
+      for (int i = 0; i < NA; ++i) { acc[i] = accnew[i]; rk.a1[i] = a7[i]; }
+      if (!grow_ok) fac = sp_min(fac, 1.0);                // no growth right after a rejection
+      grow_ok = true;
+      const double hnew = hh * fac;
+      hstep = (last && hnew < hstep) ? hstep : hnew;       // a clamped final step must not shrink h
+    } else {
+      cnt.rejected += 1;
+      hstep = hh * sp_min(fac, 1.0);
+      grow_ok = false;
+    }
+
+    if (accept && last) {
+      // ---- day boundary ------------------------------------------------------------------
+      double non[13];
+      double yraw[NL];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) yraw[i] = y[i];
+      end_day(h, c, fl, opt.dynamic_epc0, aux, y, non);
+      bool finite = true;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) finite = finite && (yraw[i] - yraw[i] == 0.0);
+      if (!finite) cnt.status |= 2;
+      io.emit(day, yraw, acc, non, c);
+      ++day;
+      if (day >= n_days) break;
+      io.forcing(day, P, E, doy);
+      io.upstream(day, us);
+      begin_day(mp, sp, c, fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+      rhs(h, y, rk.k1, rk.a1);
+      cnt.rhs_evals += 1;
+      t = 0.0;
+      day_steps = 0;
+      hstep = sp_min(hstep, T);
+    }
+  }
+}
+
+}  // namespace simplyp
