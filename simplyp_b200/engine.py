@@ -1,0 +1,114 @@
+"""Device-resident execution of the integrator: torch owns memory and streams, the C-ABI does the work.
+
+``Engine`` keeps forcing / parameters / observations resident in HBM as torch tensors and calls the
+``*_device`` entry points of ``libsimplyp_b200.so`` with raw pointers on torch's current stream.
+PyTorch is plumbing only (allocation, streams, ``torch.distributed``); every arithmetic step of the
+path runs in the hand-written kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from . import packing as pk
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """One engine per process / GPU."""
+
+    def __init__(self, device=None):
+        torch = _torch()
+        _cabi.require_device()
+        if not torch.cuda.is_available():
+            raise _cabi.SimplypError("torch sees no CUDA device: simplyp_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self._ws = None
+
+    # ------------------------------------------------------------------ helpers
+    def to_device(self, a, dtype=None):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device).contiguous()
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return torch.from_numpy(a).to(self.device)
+
+    def _workspace(self, nbytes):
+        torch = _torch()
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def free_bytes(self):
+        torch = _torch()
+        free, _total = torch.cuda.mem_get_info(self.device)
+        return int(free)
+
+    @staticmethod
+    def _shapes(forcing, member_params, sc_params):
+        D = forcing.shape[0]
+        M = member_params.shape[0]
+        if sc_params.dim() == 2:
+            sc_params = sc_params.unsqueeze(0)
+        Msc, S = sc_params.shape[0], sc_params.shape[1]
+        assert forcing.shape[1] == pk.NF and member_params.shape[1] == pk.NP_MEMBER and sc_params.shape[2] == pk.NP_SC
+        return D, M, Msc, S, sc_params
+
+    # ------------------------------------------------------------------ full output
+    def run(self, forcing, member_params, sc_params, parent_offsets, parent_ids, opt, out=None, diag=None):
+        """All tensors on this device, fp64.  Returns (out [M][S][D][25], diag [M][S][4] int64); asynchronous."""
+        torch = _torch()
+        D, M, Msc, S, sc_params = self._shapes(forcing, member_params, sc_params)
+        n_edges = int(parent_offsets[-1])
+        dims = _cabi.make_dims(M, S, D, Msc, 0, n_edges)
+        if out is None:
+            out = torch.empty((M, S, D, pk.NOUT), dtype=torch.float64, device=self.device)
+        if diag is None:
+            diag = torch.zeros((M, S, pk.NDIAG), dtype=torch.int64, device=self.device)
+        ws = self._workspace(_cabi.workspace_bytes(dims, False))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.run_device(dims, opt, forcing.data_ptr(), member_params.data_ptr(), sc_params.data_ptr(),
+                             parent_offsets, parent_ids, out.data_ptr(), diag.data_ptr(), ws.data_ptr(), stream)
+        return out, diag
+
+    # ------------------------------------------------------------------ fused statistics
+    def calibrate(self, forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc, opt,
+                  stats=None, diag=None, max_workspace_bytes=None):
+        """Returns (stats [M][V][8], diag [M][S][4]); asynchronous on the current stream.
+
+        For networks (S > 1) the per-member flux exchange buffer is M*S*D*32 bytes; members are processed
+        in chunks that keep it under ``max_workspace_bytes`` (default: half of the free HBM).
+        """
+        torch = _torch()
+        D, M, Msc, S, sc_params = self._shapes(forcing, member_params, sc_params)
+        V = obs.shape[0]
+        n_edges = int(parent_offsets[-1])
+        if stats is None:
+            stats = torch.empty((M, V, pk.NSTAT), dtype=torch.float64, device=self.device)
+        if diag is None:
+            diag = torch.zeros((M, S, pk.NDIAG), dtype=torch.int64, device=self.device)
+        chunk = M
+        if S > 1:
+            budget = max_workspace_bytes if max_workspace_bytes is not None else self.free_bytes() // 2
+            per_member = 32 * S * D
+            chunk = max(1, min(M, int(budget // max(per_member, 1))))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for m0 in range(0, M, chunk):
+                m1 = min(M, m0 + chunk)
+                dims = _cabi.make_dims(m1 - m0, S, D, 1 if Msc == 1 else (m1 - m0), V, n_edges)
+                ws = self._workspace(_cabi.workspace_bytes(dims, True))
+                scp = sc_params if Msc == 1 else sc_params[m0:m1]
+                _cabi.calibrate_device(dims, opt, forcing.data_ptr(), member_params[m0:m1].data_ptr(),
+                                       scp.data_ptr(), parent_offsets, parent_ids, obs.data_ptr(),
+                                       obs_desc.data_ptr(), stats[m0:m1].data_ptr(), diag[m0:m1].data_ptr(),
+                                       ws.data_ptr(), stream)
+        return stats, diag

@@ -136,7 +136,7 @@ def read_input_data(params_fpath):
     for SC in p["SC_list"]:
         frames = [d[SC] for d in (q_obs, chem_obs) if SC in d]
         if frames:
-            obs_dict[int(SC)] = pd.concat(frames, axis=1)
+            obs_dict[int(SC)] = pd.concat(frames, axis=1, sort=True)
 
     return (p_SU, dynamic_options, p, p_LU, p_SC, p_struc, met_df, obs_dict)
 

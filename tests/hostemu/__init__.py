@@ -1,0 +1,56 @@
+"""Test-only host build of the kernels' per-thread arithmetic (see hostemu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(HERE, "hostemu.cpp")
+LIB = os.path.join(HERE, "libsimplyp_hostemu.so")
+DEPS = [SRC, os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_core.cuh"),
+        os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_thread.cuh"),
+        os.path.join(ROOT, "include", "simplyp_b200.h")]
+
+_lib = None
+
+
+def build(force=False):
+    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS)
+    if stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-o", LIB, SRC])
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt):
+    """Same contract as simplyp_b200._cabi.run_host, executed by the host build (tests only)."""
+    from simplyp_b200 import _cabi, packing as pk
+    lib = load()
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    member_params = np.ascontiguousarray(member_params, dtype=np.float64)
+    sc_params = np.ascontiguousarray(sc_params, dtype=np.float64)
+    if sc_params.ndim == 2:
+        sc_params = sc_params[None]
+    M, D = member_params.shape[0], forcing.shape[0]
+    Msc, S = sc_params.shape[0], sc_params.shape[1]
+    po = np.ascontiguousarray(parent_offsets, dtype=np.int32)
+    pid = np.ascontiguousarray(parent_ids, dtype=np.int32)
+    if pid.size == 0:
+        pid = np.zeros(1, dtype=np.int32)
+    dims = _cabi.make_dims(M, S, D, Msc, 0, int(po[-1]))
+    out = np.zeros((M, S, D, pk.NOUT))
+    diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
+    vp = C.c_void_p
+    lib.hostemu_run(C.byref(dims), C.byref(opt), forcing.ctypes.data_as(vp), member_params.ctypes.data_as(vp),
+                    sc_params.ctypes.data_as(vp), po.ctypes.data_as(vp), pid.ctypes.data_as(vp),
+                    out.ctypes.data_as(vp), diag.ctypes.data_as(vp))
+    return out, diag

@@ -1,0 +1,189 @@
+"""GPU tier: the CUDA path, called through the C-ABI (ctypes), against the oracle and the live-reference
+fixtures.  Parity bound: relative error <= 1e-5 on daily flows and concentrations at the product's default
+tolerances (rtol=1e-7, atol=1e-10) versus the reference's odeint path run at tight tolerance
+(rtol=1e-10, atol=1e-13); see tests/parity.py."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests import parity
+from tests.util import max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from simplyp_b200 import _cabi
+    _cabi.require_device()          # fails loudly if the extension or the GPU is missing: no fallback
+    return _cabi
+
+
+@pytest.mark.parametrize("dy", ["n", "y"])
+def test_tarland_2004_vs_reference(cabi, golden_dir, dy):
+    parity.check_tarland(cabi.run_host, golden_dir, dy)
+
+
+def test_branching_network_vs_reference(cabi, golden_dir):
+    parity.check_network(cabi.run_host, golden_dir)
+
+
+def test_ensemble_series_vs_reference(cabi, golden_dir):
+    worst = parity.check_ensemble_series(cabi.run_host, golden_dir)
+    assert worst <= parity.PARITY
+
+
+def test_drop_in_run_simply_p(cabi, golden_dir):
+    """The reference-facing entry point: same return tuple, column layout, mutations, Kf."""
+    import simplyp_b200 as sp
+    from simplyp_b200 import tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    TC, R, Kf, info = sp.run_simply_p(met, p_struc, p_SU, p_LU, p_SC, p, dyn, verbose=False)
+    z = np.load(os.path.join(golden_dir, "ref_tarland2004.npz"))
+    assert list(TC[1].columns) == list(z["dyny_tight_tc_cols"]) and len(TC[1].columns) == 20
+    assert list(R[1].columns) == list(z["dyny_tight_r_cols"]) and len(R[1].columns) == 17
+    assert Kf == 0.00011315280464216634
+    assert {"EPC0_0", "Plab0", "TDPs0"} <= set(p_LU.index) and {"f_A", "f_NC_A", "NC_type"} <= set(p_SC.index)
+    assert p_SC.loc["NC_type", 1] == "None"
+    assert info["nfe"] > 0 and info["message"].startswith("Integration successful")
+    want = pd.DataFrame(z["dyny_tight_r"], columns=list(z["dyny_tight_r_cols"]))
+    for c in ("Q_cumecs", "SS_mgl", "TDP_mgl", "PP_mgl", "TP_mgl", "SRP_mgl"):
+        assert max_rel(R[1][c].to_numpy(), want[c].to_numpy()) <= 1e-5, c
+    # goodness-of-fit table of the reference on the reference run vs ours on our run
+    gof = json.load(open(os.path.join(golden_dir, "ref_gof.json")))["dyny_tight"]
+    got = sp.goodness_of_fit_stats(p_SU, R, obs)
+    assert list(got.index) == gof["index"]
+    assert np.allclose(got.to_numpy(float)[:, :7], np.array(gof["values"])[:, :7], rtol=2e-5, atol=2e-6)
+
+
+def test_fused_statistics_vs_reference(cabi, golden_dir):
+    """Calibration mode: on-device NSE / log-NSE / r2 / bias / nRMSD vs the reference's goodness_of_fit_stats
+    on its own (tight-tolerance) runs of the same Latin-hypercube members; log-likelihood vs the oracle."""
+    from oracle import simplyp_oracle as orc
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    z, samples = parity.ensemble_fixture(golden_dir)
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, None)
+    assert [l[1] for l in labels] == ["Q", "SS", "TDP", "PP", "TP", "SRP"]
+    stats, diag = cabi.calibrate_host(pk.forcing_matrix(met), member, sc, topo.parent_offsets, topo.parent_ids,
+                                      obs_m, desc, opt)
+    assert not np.any(diag[..., 3])
+    gof = z["gof"]     # [M][6 vars][N obs, NSE, log NSE, Spearman, r2, bias, nRMSD]
+    cols = [str(c) for c in z["cols"]]
+    for i in range(member.shape[0]):
+        for v, (_sc, var) in enumerate(labels):
+            want = gof[i, v]
+            got = stats[i, v]
+            assert got[0] == want[0], (i, var)                                   # n pairs
+            for k_got, k_want, name in ((1, 1, "NSE"), (2, 2, "log NSE"), (4, 4, "r2"), (5, 5, "bias"), (6, 6, "nRMSD")):
+                tol = 2e-5 * max(1.0, abs(want[k_want]))
+                assert abs(got[k_got] - want[k_want]) <= tol, (i, var, name, got[k_got], want[k_want])
+        # Gaussian log-likelihood against the oracle's restatement on the reference series
+        for v, var, col in ((0, "Q", "Q_cumecs"), (2, "TDP", "TDP_mgl")):
+            o = obs[1][var].reindex(met.index).to_numpy(float)
+            sim = z["series"][i, :, cols.index(col)]
+            m = member[i, pk.MEMBER_INDEX["err_m:" + var]]
+            want = orc.gaussian_log_likelihood(o, sim, m)
+            assert abs(stats[i, v, 3] - want) <= 1e-4 * max(1.0, abs(want)), (i, var, stats[i, v, 3], want)
+
+
+def test_device_pointer_api_matches_host_api(cabi, golden_dir):
+    import torch
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from simplyp_b200.engine import Engine
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    met = met.iloc[:90]
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(257, seed=3)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
+    out_h, diag_h = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    st_h, _ = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+    eng = Engine(0)
+    out_d, diag_d = eng.run(eng.to_device(forcing), eng.to_device(member), eng.to_device(sc), topo.parent_offsets,
+                            topo.parent_ids, opt)
+    st_d, _ = eng.calibrate(eng.to_device(forcing), eng.to_device(member), eng.to_device(sc), topo.parent_offsets,
+                            topo.parent_ids, eng.to_device(obs_m), eng.to_device(desc), opt)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_h, out_d.cpu().numpy())          # bitwise: same kernel, same inputs
+    assert np.array_equal(diag_h, diag_d.cpu().numpy())
+    assert np.array_equal(st_h, st_d.cpu().numpy())
+    # calibration statistics are consistent with the full-output series of the same run
+    q = out_h[:, 0, :, 5] * 51.7 * 1000 / 86400
+    o = obs_m[0]
+    ok = ~np.isnan(o)
+    nse = 1 - ((o[ok] - q[:, ok]) ** 2).sum(axis=1) / ((o[ok] - o[ok].mean()) ** 2).sum()
+    assert np.allclose(nse, st_h[:, 0, 1], rtol=1e-10, atol=1e-10)
+
+
+def test_full_size_ensemble_properties(cabi):
+    """BASELINE config 2 at full size (10^4 members, 2004): properties that need no oracle.
+    (a) shard invariance: any contiguous block of members integrated alone is bitwise the same;
+    (b) the reach volume/flow invariant Vr = L/(a_Q 86400) Qr^(1-b_Q) implied by ode_f (:127-131) holds;
+    (c) statistics converge under tolerance refinement (default vs 10x tighter)."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(10000, seed=20260101)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
+    args = (topo.parent_offsets, topo.parent_ids, obs_m, desc)
+    st, dg = cabi.calibrate_host(forcing, member, sc, *args, opt)
+    assert np.all(np.isfinite(st[..., :3])) and not np.any(dg[..., 3])
+    lo, hi = 3331, 5017
+    st2, dg2 = cabi.calibrate_host(forcing, member[lo:hi], sc[lo:hi], *args, opt)
+    assert np.array_equal(st2, st[lo:hi]) and np.array_equal(dg2, dg[lo:hi])
+    opt_t = spm.make_options(p_SU, p, dyn, topo, rtol=opt.rtol / 10, atol=opt.atol / 10)
+    st3, _ = cabi.calibrate_host(forcing, member[:2048], sc[:2048], *args, opt_t)
+    sse, sse3 = st[:2048, :, 7], st3[:, :, 7]
+    assert np.max(np.abs(sse - sse3) / np.abs(sse3)) < 2e-5
+    out, dgo = cabi.run_host(forcing[:120], member[:512], sc[:512], topo.parent_offsets, topo.parent_ids, opt)
+    Qr, Vr = out[:, 0, :, 4], out[:, 0, :, 3]
+    aQ, bQ = member[:512, pk.MEMBER_INDEX["a_Q"]][:, None], member[:512, pk.MEMBER_INDEX["b_Q"]][:, None]
+    L = sc[:512, 0, pk.SC_INDEX["L_reach"]][:, None]
+    assert np.max(np.abs(Vr - L / (aQ * 86400.0) * Qr ** (1 - bQ)) / Vr) < 1e-5
+
+
+def test_synthetic_network_vs_oracle(cabi):
+    """64-reach branching network (config-3 generator, small) against the oracle on a 40-day window."""
+    from oracle import simplyp_oracle as orc
+    from simplyp_b200 import model as spm, packing as pk, synthetic, tarland
+    p_SU, dyn, p, p_LU, p_SC0, p_struc0, met, obs = tarland.load(dynamic="y")
+    p, p_SC, p_struc = synthetic.random_network(p, p_SC0[1], n_sc=64, seed=3)
+    met = met.iloc[:40]
+    TC, R, diag, met = parity.run_single(cabi.run_host, (p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs))
+    TCo, Ro, Kf, _ = orc.run_simply_p(met, p_struc, p_SU, p_LU, p_SC, p, dyn, rtol=1e-10, atol=1e-13, mxstep=50000)
+    for SC in p["SC_list"]:
+        parity.assert_frames_close(TC[SC], R[SC], TCo[SC], Ro[SC], "synthetic SC %d" % SC)
+
+
+def test_edge_cases(cabi):
+    from simplyp_b200 import model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="n")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    member, sc, forcing = pk.member_vector(p, p_LU)[None], pk.sc_matrix(p_SC, topo.sc_ids)[None], pk.forcing_matrix(met)
+    out0, _ = cabi.run_host(forcing[:0], member, sc, topo.parent_offsets, topo.parent_ids, opt)    # empty period
+    assert out0.shape == (1, 1, 0, 25)
+    out1, _ = cabi.run_host(forcing[:1], member, sc, topo.parent_offsets, topo.parent_ids, opt)    # one day
+    out3, _ = cabi.run_host(forcing[:3], member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert np.array_equal(out1[0, 0, 0], out3[0, 0, 0])
+    # a dry spell: zero rain and zero PET for 200 days keeps every state finite and flow positive
+    dry = forcing.copy()
+    dry[:, 0] = 0.0
+    dry[:, 1] = 0.0
+    outd, dg = cabi.run_host(dry[:200], member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert np.all(np.isfinite(outd)) and np.all(outd[0, 0, :, 5] > 0) and not np.any(dg[..., 3])
+    # bad arguments come back as errors, not crashes
+    with pytest.raises(cabi.SimplypError):
+        cabi.run_host(forcing, member, sc, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), opt)
