@@ -18,6 +18,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/simplyp_b200.h"
 
@@ -33,9 +34,14 @@ namespace simplyp {
 // number of live ODE states and of daily accumulators (ode_f's y[0..11] split by role)
 //   live: VsA VsS Vg Vr Qr Msus TDPr PPr      (y[0..4], y[6], y[8], y[10])
 //   acc : Qr_av Msus_out TDPr_out PPr_out     (y[5], y[7], y[9], y[11]); zero at day start (:618)
-constexpr int NL = 8;
+//   The reach volume Vr is NOT integrated: ode_f's dVr/dt = net and dQr/dt = net*a_Q*Qr^b_Q*86400/((1-b_Q)*L)
+//   (:127-131) imply d/dt[Vr - L/(a_Q*86400) * Qr^(1-b_Q)] = 0, and the reference's initial condition
+//   Vr0 = L/(a_Q*Qr0^b_Q*86400)*Qr0 (:457-459) lies on that curve, so Vr == L/(a_Q*86400)*Qr^(1-b_Q) for all t.
+//   The kernel carries Qr only, uses Qr/Vr = (a_Q*86400/L)*Qr^b_Q in the mass equations and reports
+//   Vr from the identity (the LSODA oracle integrates Vr; both agree to the solver tolerance).
+constexpr int NL = 7;
 constexpr int NA = 4;
-enum { iVsA = 0, iVsS, iVg, iVr, iQr, iMsus, iTDPr, iPPr };
+enum { iVsA = 0, iVsS, iVg, iQr, iMsus, iTDPr, iPPr };
 
 // Constants of the RHS that are fixed within one day.  Kept in registers.
 struct Hot {
@@ -44,6 +50,7 @@ struct Hot {
   double fA, fS, beta;
   double qin0;           // Qq + Qr_US
   double kQ, bQ, kM;     // a_Q*86400/((1-b_Q)*L_reach), b_Q, k_M
+  double cR;             // a_Q*86400/L_reach: Qr/Vr = cR*Qr^b_Q
   double cM, MsusUS;     // sediment source coefficient, upstream sediment
   double tA, tS, tG, t0; // TDP: coefficients of QsA, QsS, Qg and the constant source
   double cP, PPUS;       // PP source coefficient, upstream PP
@@ -82,6 +89,101 @@ struct Flags {
 SP_HD double sp_max(double a, double b) { return a > b ? a : b; }
 SP_HD double sp_min(double a, double b) { return a < b ? a : b; }
 
+// ---- branch-free fp64 elementary functions for the ranges this model visits -------------------
+// The CUDA math library's exp/log/division carry special-case branches (and, for division, a
+// call to a slow path) that cost issue slots and registers in a kernel whose critical path is one
+// long dependent fp64 chain.  These versions assume finite, normal arguments (|x| < 700 for exp,
+// x > 0 for log, normal divisor) — a NaN still propagates as NaN, which the step control rejects.
+// Polynomials are evaluated with Estrin's scheme (short dependency chains).  Accuracy ~1-2 ulp.
+SP_HD long long sp_d2ll(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(x);
+#else
+  long long b; memcpy(&b, &x, 8); return b;
+#endif
+}
+SP_HD double sp_ll2d(long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+SP_HD double sp_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 good bits
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
+// ~7 significant digits: only for the error norm and the step-size factor
+SP_HD double sp_rcp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
+#else
+  return 1.0 / x;
+#endif
+}
+
+SP_HD double sp_exp(double x) {
+  // x = k ln2 + r, |r| <= ln2/2 ; e^r by its degree-12 Taylor polynomial (remainder < 2e-16).
+  // Arguments are clamped to [-700, 700] (e^-700 ~ 1e-304 stands in for an underflow to 0).
+  x = sp_min(sp_max(x, -700.0), 700.0);
+  const double kf = rint(x * 1.4426950408889634074);
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p01 = 1.0 + r;
+  const double p23 = fma(r, 1.0 / 6.0, 0.5);
+  const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double pc = 1.0 / 479001600.0;
+  const double q0 = fma(r2, p23, p01);          // terms 0..3
+  const double q1 = fma(r2, p67, p45);          // terms 4..7  (times r^4)
+  const double q2 = fma(r2, pab, p89);          // terms 8..11 (times r^8)
+  const double lo = fma(r4, q1, q0);
+  const double hi = fma(r4, pc, q2);            // pc carries r^12 = r^8 * r^4
+  const double p = fma(r8, hi, lo);
+  // scale by 2^k through the exponent field (k in [-1000, 1000] here)
+  return sp_ll2d(sp_d2ll(p) + ((long long)kf << 52));
+}
+
+SP_HD double sp_log(double x) {
+  // x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(f), f = (m-1)/(m+1), |f| <= 0.1716
+  long long b = sp_d2ll(x);
+  long long e = ((b >> 52) & 0x7ff) - 1023;
+  b = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+  double m = sp_ll2d(b);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double f = (m - 1.0) * sp_rcp(m + 1.0);
+  const double s = f * f, s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
+  // 1 + s/3 + s^2/5 + ... + s^10/21
+  const double a01 = fma(s, 1.0 / 3.0, 1.0);
+  const double a23 = fma(s, 1.0 / 7.0, 1.0 / 5.0);
+  const double a45 = fma(s, 1.0 / 11.0, 1.0 / 9.0);
+  const double a67 = fma(s, 1.0 / 15.0, 1.0 / 13.0);
+  const double a89 = fma(s, 1.0 / 19.0, 1.0 / 17.0);
+  const double aa = 1.0 / 21.0;
+  const double c0 = fma(s2, a23, a01);
+  const double c1 = fma(s2, a67, a45);
+  const double c2 = fma(s2, aa, a89);
+  const double poly = fma(s8, c2, fma(s4, c1, c0));
+  const double ed = (double)e;
+  return fma(ed, 6.93147180369123816490e-01, fma(2.0 * f, poly, ed * 1.90821492927058770002e-10));
+}
+
 // f_x(x, thr, 0.01) expressed on u = (x-thr)/(thr*0.01): 0 for u<0, 1 for u>1, 3u^2-2u^3 between.
 SP_HD double gate(double u) {
   u = sp_min(sp_max(u, 0.0), 1.0);
@@ -91,13 +193,13 @@ SP_HD double gate(double u) {
 // ------------------------------------------------------------------------------------------
 // ode_f: derivatives of the 8 live states; the 4 accumulator derivatives come out separately.
 SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&da)[NA]) {
-  const double VsA = y[iVsA], VsS = y[iVsS], Vg = y[iVg], Vr = y[iVr], Qr = y[iQr];
+  const double VsA = y[iVsA], VsS = y[iVsS], Vg = y[iVg], Qr = y[iQr];
   // soil boxes (:105-110)
   const double xA = VsA - c.fc, xS = VsS - c.fc;
   const double QsA = xA * gate(xA * c.inv_fcd) * c.inv_TsA;
   const double QsS = xS * gate(xS * c.inv_fcd) * c.inv_TsS;
-  dy[iVsA] = c.Pin - c.aE * (1.0 - exp(-c.mu * VsA)) - QsA;
-  dy[iVsS] = c.Pin - c.aE * (1.0 - exp(-c.mu * VsS)) - QsS;
+  dy[iVsA] = c.Pin - c.aE * (1.0 - sp_exp(-c.mu * VsA)) - QsA;
+  dy[iVsS] = c.Pin - c.aE * (1.0 - sp_exp(-c.mu * VsS)) - QsS;
   // groundwater (:121-124)
   const double xg = Vg * c.inv_Tg - c.Qg_min;
   const double Qg = c.Qg_min + gate(xg * c.inv_Qgd) * xg;
@@ -105,14 +207,13 @@ SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&d
   dy[iVg] = c.beta * soil - Qg;
   // reach (:127-132); Qr^b_Q and Qr^k_M share one logarithm
   const double net = c.qin0 + (1.0 - c.beta) * soil + Qg - Qr;
-  const double lq = log(Qr);
-  const double qb = exp(c.bQ * lq);
-  const double qk = exp(c.kM * lq);
+  const double lq = sp_log(Qr);
+  const double qb = sp_exp(c.bQ * lq);
+  const double qk = sp_exp(c.kM * lq);
   dy[iQr] = net * c.kQ * qb;
-  dy[iVr] = net;
   da[0] = Qr;
-  // outflow rate of the reach, 1/day
-  const double r = Qr / Vr;
+  // outflow rate of the reach, 1/day: Qr/Vr with Vr on its invariant curve
+  const double r = c.cR * qb;
   // sediment (:138-147)
   const double oM = y[iMsus] * r;
   dy[iMsus] = c.cM * qk + c.MsusUS - oM;
@@ -127,19 +228,24 @@ SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&d
   da[3] = oP;
 }
 
+// Reach volume on the invariant curve (reported as the 'Vr' output column).
+SP_HD double reach_volume(const Hot& c, double Qr) { return Qr / (c.cR * sp_exp(c.bQ * sp_log(Qr))); }
+
 // ------------------------------------------------------------------------------------------
 // discretized_soilP (:39-56).  pnet = P_netInput*A_catch*100/365.
 SP_HD void soilp_update(double pnet, double KfMsoil, double EPC0, double Qs, double Qq, double Vs,
                         double& TDPs, double& Plab) {
   const double a = pnet + KfMsoil * EPC0;
-  const double b = (KfMsoil + Qs + Qq) / Vs;
-  const double ab = a / b;
-  const double e = exp(-b);
+  const double iVs = 1.0 / Vs;
+  const double b = (KfMsoil + Qs + Qq) * iVs;
+  const double ib = sp_rcp(b);
+  const double ab = a * ib;
+  const double e = sp_exp(-b);
   TDPs = ab + (TDPs - ab) * e;                                   // :44
   double sorp = 0.0;
   if (Vs > 0.0) {                                                // :50
-    const double ab0 = a / (b * Vs);
-    sorp = KfMsoil * (ab0 - EPC0 + (1.0 / b) * (TDPs / Vs - ab0) * (1.0 - e));   // :51 (updated TDPs)
+    const double ab0 = ab * iVs;                                 // a/(b*Vs)
+    sorp = KfMsoil * (ab0 - EPC0 + ib * (TDPs * iVs - ab0) * (1.0 - e));   // :51 (updated TDPs)
   }
   Plab = Plab + sorp;                                            // :54
 }
@@ -192,6 +298,7 @@ SP_HD void setup_thread(const double* mp, const double* sp, double A_qr0, int nc
   h.beta = mp[SIMPLYP_P_BETA];
   const double aQ = mp[SIMPLYP_P_A_Q], bQ = mp[SIMPLYP_P_B_Q];
   h.kQ = aQ * 86400.0 / ((1.0 - bQ) * sp[SIMPLYP_SC_L_REACH]);   // :130
+  h.cR = aQ * 86400.0 / sp[SIMPLYP_SC_L_REACH];
   h.bQ = bQ;
   h.kM = mp[SIMPLYP_P_K_M];
   h.tG = mp[SIMPLYP_P_TDPG] * A;                                 // UC_Cinv(TDPg, A_catch), :163
@@ -246,8 +353,7 @@ SP_HD void setup_thread(const double* mp, const double* sp, double A_qr0, int nc
   y[iVsA] = fc;
   y[iVsS] = fc;
   y[iVg] = mp[SIMPLYP_P_BETA] * Qr0 * mp[SIMPLYP_P_T_G];
-  y[iQr] = Qr0;
-  y[iVr] = sp[SIMPLYP_SC_L_REACH] / (aQ * pow(Qr0, bQ) * 86400.0) * Qr0;
+  y[iQr] = Qr0;                                                  // Vr0 (:457-459) lies on the invariant curve
   y[iMsus] = 0.0;
   y[iTDPr] = 0.0;
   y[iPPr] = 0.0;
@@ -400,7 +506,7 @@ SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc
   for (int i = 0; i < NL; ++i) {
     const double err = hh * (e1 * rk.k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k7[i]);
     const double sc = atol + rtol * sp_max(fabs(y[i]), fabs(ynew[i]));
-    const double q = err / sc;
+    const double q = err * sp_rcp_fast(sc);
     s += q * q;
   }
 #pragma unroll
@@ -408,7 +514,7 @@ SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc
     accnew[i] = acc[i] + hh * sb[i];
     const double err = hh * (se[i] + e7 * a7[i]);
     const double sc = atol + rtol * sp_max(fabs(acc[i]), fabs(accnew[i]));
-    const double q = err / sc;
+    const double q = err * sp_rcp_fast(sc);
     s += q * q;
   }
   const double en = sqrt(s * (1.0 / (NL + NA)));
@@ -419,7 +525,11 @@ SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc
 SP_HD double step_factor(double en) {
   if (!(en > 1e-30)) return 5.0;
   if (!(en < 1e30)) return 0.2;
+#if defined(__CUDA_ARCH__)
+  const double f = 0.9 * (double)exp2f(-0.2f * __log2f((float)en));
+#else
   const double f = 0.9 * exp(-0.2 * log(en));
+#endif
   return sp_min(5.0, sp_max(0.2, f));
 }
 

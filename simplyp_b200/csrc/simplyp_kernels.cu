@@ -103,13 +103,14 @@ struct RunIO : IOBase {
       us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
     }
   }
-  __device__ __forceinline__ void emit(int day, const double (&y)[NL], const double (&acc)[NA],
+  __device__ __forceinline__ bool wants_vr() const { return true; }
+  __device__ __forceinline__ void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
                                        const double (&non)[13], const Cold&) const {
     double* row = a.out + (((size_t)m * a.S + s) * a.D + day) * SIMPLYP_NOUT;
     row[SIMPLYP_O_VSA] = y[iVsA];
     row[SIMPLYP_O_VSS] = y[iVsS];
     row[SIMPLYP_O_VG] = y[iVg];
-    row[SIMPLYP_O_VR] = y[iVr];
+    row[SIMPLYP_O_VR] = Vr;
     row[SIMPLYP_O_QR_END] = y[iQr];
     row[SIMPLYP_O_QR] = acc[0];
     row[SIMPLYP_O_MSUS_END] = y[iMsus];
@@ -144,7 +145,8 @@ struct CalIO : IOBase {
       us[3] += __ldcg(row + 3);
     }
   }
-  __device__ __forceinline__ void emit(int day, const double (&)[NL], const double (&acc)[NA],
+  __device__ __forceinline__ bool wants_vr() const { return false; }
+  __device__ __forceinline__ void emit(int day, const double (&)[NL], double, const double (&acc)[NA],
                                        const double (&)[13], const Cold& c) const {
     if (a.flux != nullptr) {
       double* row = a.flux + (((size_t)m * a.S + s) * a.D + day) * 4;

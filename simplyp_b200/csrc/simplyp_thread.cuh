@@ -29,7 +29,7 @@ struct ThreadCounters {
 // IO policy concept:
 //   void forcing(int day, double& P, double& E, double& doy);
 //   void upstream(int day, double (&us)[4]);     // area-scaled Qr, Msus, TDP, PP of the parents, summed
-//   void emit(int day, const double (&y)[NL], const double (&acc)[NA], const double (&non)[13],
+//   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
 //             const Cold& c);                    // y holds the raw end-of-day ODE states
 template <class IO>
 SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int nc_last,
@@ -73,8 +73,8 @@ SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int n
     day_steps += 1;
 
     bool accept = en <= 1.0;
-    if (!accept && day_steps >= opt.max_steps_per_day) {   // give up on error control for this day
-      accept = true;
+    if (!accept && (day_steps >= opt.max_steps_per_day || hh < 1e-12 * T)) {
+      accept = true;           // give up on error control for this step: guarantees forward progress
       cnt.status |= 1;
     }
     double fac = step_factor(en);
@@ -105,7 +105,7 @@ SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int n
 #pragma unroll
       for (int i = 0; i < NL; ++i) finite = finite && (yraw[i] - yraw[i] == 0.0);
       if (!finite) cnt.status |= 2;
-      io.emit(day, yraw, acc, non, c);
+      io.emit(day, yraw, io.wants_vr() ? reach_volume(h, yraw[iQr]) : 0.0, acc, non, c);
       ++day;
       if (day >= n_days) break;
       io.forcing(day, P, E, doy);

@@ -32,9 +32,11 @@ struct HostIO {
       us[3] += row[SIMPLYP_O_PP_FLUX];
     }
   }
-  void emit(int day, const double (&y)[NL], const double (&acc)[NA], const double (&non)[13], const Cold&) const {
+  bool wants_vr() const { return true; }
+  void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
+            const Cold&) const {
     double* row = out + (((size_t)m * S + s) * D + day) * SIMPLYP_NOUT;
-    row[0] = y[iVsA]; row[1] = y[iVsS]; row[2] = y[iVg]; row[3] = y[iVr]; row[4] = y[iQr]; row[5] = acc[0];
+    row[0] = y[iVsA]; row[1] = y[iVsS]; row[2] = y[iVg]; row[3] = Vr; row[4] = y[iQr]; row[5] = acc[0];
     row[6] = y[iMsus]; row[7] = acc[1]; row[8] = y[iTDPr]; row[9] = acc[2]; row[10] = y[iPPr]; row[11] = acc[3];
     for (int i = 0; i < 13; ++i) row[12 + i] = non[i];
   }
