@@ -232,6 +232,10 @@ int64_t simplyp_launch_count(void);
  * roofline denominator MEASURED_PEAKS.json does not carry.  Returns <0 on error. */
 double simplyp_measure_fp64_peak(int device, int repeats);
 
+/* Cycles per DEPENDENT DFMA (one warp, one chain): the fp64 pipeline latency that bounds a
+ * single thread's progress when the ensemble is too small to fill the machine. */
+double simplyp_measure_fp64_latency(int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ EXPORTS = [
     "simplyp_default_options", "simplyp_topology_levels", "simplyp_workspace_bytes",
     "simplyp_run_device", "simplyp_calibrate_device", "simplyp_run_host", "simplyp_calibrate_host",
     "simplyp_release_cache", "simplyp_launch_count", "simplyp_measure_fp64_peak",
+    "simplyp_measure_fp64_latency",
 ]
 
 
@@ -79,6 +80,8 @@ def load():
     lib.simplyp_launch_count.restype = C.c_int64
     lib.simplyp_measure_fp64_peak.argtypes = [C.c_int, C.c_int]
     lib.simplyp_measure_fp64_peak.restype = C.c_double
+    lib.simplyp_measure_fp64_latency.argtypes = [C.c_int]
+    lib.simplyp_measure_fp64_latency.restype = C.c_double
     if lib.simplyp_abi_version() != 1:
         raise SimplypError("ABI version mismatch")
     _lib = lib
@@ -222,6 +225,11 @@ def workspace_bytes(dims, calibrate):
 
 def launch_count():
     return int(load().simplyp_launch_count())
+
+
+def measure_fp64_latency(device=0):
+    require_device()
+    return float(load().simplyp_measure_fp64_latency(device))
 
 
 def measure_fp64_peak(device=0, repeats=3):

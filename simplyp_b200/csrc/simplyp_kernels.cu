@@ -298,6 +298,19 @@ __global__ void fp64_peak_kernel(double* sink, int iters, double a, double b) {
   if (r == 123.456) sink[0] = r;
 }
 
+// one warp, one dependent DFMA chain: cycles per dependent DFMA = the fp64 pipe latency
+__global__ void fp64_latency_kernel(double* sink, long long* cycles, int iters, double a, double b) {
+  double x = threadIdx.x;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) x = fma(x, a, b);
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  if (x == 123.456) sink[0] = x;
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<int>& lvl) {
   lvl.assign(S, 0);
@@ -636,6 +649,28 @@ void simplyp_release_cache(void) {
 }
 
 int64_t simplyp_launch_count(void) { return g_launches.load(); }
+
+double simplyp_measure_fp64_latency(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+    return -1.0;
+  }
+  cudaSetDevice(device);
+  double* sink = nullptr;
+  long long* cyc = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess || cudaMalloc(&cyc, 8) != cudaSuccess) return -1.0;
+  const int iters = 4096;
+  long long h = 0;
+  for (int r = 0; r < 2; ++r) {
+    fp64_latency_kernel<<<1, 32>>>(sink, cyc, iters, 0.999999, 1e-9);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  }
+  g_launches.fetch_add(2);
+  cudaFree(sink);
+  cudaFree(cyc);
+  return (double)h / (16.0 * iters);
+}
 
 double simplyp_measure_fp64_peak(int device, int repeats) {
   int n = 0;
