@@ -135,10 +135,9 @@ SP_HD double sp_rcp_fast(double x) {
 #endif
 }
 
-SP_HD double sp_exp(double x) {
-  // x = k ln2 + r, |r| <= ln2/2 ; e^r by its degree-12 Taylor polynomial (remainder < 2e-16).
-  // Arguments are clamped to [-700, 700] (e^-700 ~ 1e-304 stands in for an underflow to 0).
-  x = sp_min(sp_max(x, -700.0), 700.0);
+// e^x for |x| < 700, no range check (the RHS arguments -mu*Vs, b_Q*ln Qr, k_M*ln Qr are far inside).
+SP_HD double sp_exp_core(double x) {
+  // x = k ln2 + r, |r| <= ln2/2 ; e^r by its degree-12 Taylor polynomial (remainder < 2e-16)
   const double kf = rint(x * 1.4426950408889634074);
   double r = fma(kf, -6.93147180369123816490e-01, x);
   r = fma(kf, -1.90821492927058770002e-10, r);
@@ -156,9 +155,13 @@ SP_HD double sp_exp(double x) {
   const double lo = fma(r4, q1, q0);
   const double hi = fma(r4, pc, q2);            // pc carries r^12 = r^8 * r^4
   const double p = fma(r8, hi, lo);
-  // scale by 2^k through the exponent field (k in [-1000, 1000] here)
+  // scale by 2^k through the exponent field
   return sp_ll2d(sp_d2ll(p) + ((long long)kf << 52));
 }
+
+// Range-checked variant for the once-a-day algebra: arguments are clamped to [-700, 700]
+// (e^-700 ~ 1e-304 stands in for an underflow to 0).
+SP_HD double sp_exp(double x) { return sp_exp_core(sp_min(sp_max(x, -700.0), 700.0)); }
 
 SP_HD double sp_log(double x) {
   // x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(f), f = (m-1)/(m+1), |f| <= 0.1716
@@ -198,8 +201,8 @@ SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&d
   const double xA = VsA - c.fc, xS = VsS - c.fc;
   const double QsA = xA * gate(xA * c.inv_fcd) * c.inv_TsA;
   const double QsS = xS * gate(xS * c.inv_fcd) * c.inv_TsS;
-  dy[iVsA] = c.Pin - c.aE * (1.0 - sp_exp(-c.mu * VsA)) - QsA;
-  dy[iVsS] = c.Pin - c.aE * (1.0 - sp_exp(-c.mu * VsS)) - QsS;
+  dy[iVsA] = c.Pin - c.aE * (1.0 - sp_exp_core(-c.mu * VsA)) - QsA;
+  dy[iVsS] = c.Pin - c.aE * (1.0 - sp_exp_core(-c.mu * VsS)) - QsS;
   // groundwater (:121-124)
   const double xg = Vg * c.inv_Tg - c.Qg_min;
   const double Qg = c.Qg_min + gate(xg * c.inv_Qgd) * xg;
@@ -208,8 +211,8 @@ SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&d
   // reach (:127-132); Qr^b_Q and Qr^k_M share one logarithm
   const double net = c.qin0 + (1.0 - c.beta) * soil + Qg - Qr;
   const double lq = sp_log(Qr);
-  const double qb = sp_exp(c.bQ * lq);
-  const double qk = sp_exp(c.kM * lq);
+  const double qb = sp_exp_core(c.bQ * lq);
+  const double qk = sp_exp_core(c.kM * lq);
   dy[iQr] = net * c.kQ * qb;
   da[0] = Qr;
   // outflow rate of the reach, 1/day: Qr/Vr with Vr on its invariant curve
