@@ -61,6 +61,8 @@ struct KArgs {
   const double* obs_const;      // cal: [V][8]
   double* stats;                // cal: [M][V][8]
   double* flux;                 // cal, S>1: [M][S][D][4]
+  int* progress;                // S>1: [M][S] days completed (release/acquire flags of the routing wavefront)
+  int* ticket;                  // S>1: block ticket counter (virtual block order = dispatch order)
 };
 
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
@@ -75,6 +77,25 @@ struct IOBase {
   const double* scp_member;  // this member's [S][NP_SC] block
   __device__ IOBase(const KArgs& a_, int m_, int s_)
       : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC) {}
+
+  // Routing wavefront: day `d` of this reach may start once every directly-upstream reach of the same
+  // member has published day `d` (acquire load pairs with the release store in publish()).
+  __device__ __forceinline__ bool ready(int day) const {
+    if (a.progress == nullptr) return true;
+    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int* flag = a.progress + (size_t)m * a.S + a.parent_ids[e];
+      int done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(flag) : "memory");
+      if (done <= day) return false;
+    }
+    return true;
+  }
+  __device__ __forceinline__ void publish(int day) const {
+    if (a.progress == nullptr) return;
+    int* flag = a.progress + (size_t)m * a.S + s;
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(day + 1) : "memory");
+  }
 
   __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy) const {
     const double2 f = __ldg(reinterpret_cast<const double2*>(a.forcing + (size_t)day * SIMPLYP_NF));
@@ -213,7 +234,17 @@ struct CalIO : IOBase {
 template <bool CAL>
 __global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
   extern __shared__ double smem_cold[];
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // Networks: blocks take a ticket so that "lower index" means "dispatched earlier"; a reach only ever
+  // waits for reaches of lower topological level, which sit at lower indices, so a waiting block can only
+  // wait for blocks that are already running or finished (no deadlock even if the grid is not co-resident).
+  __shared__ unsigned s_vblock;
+  unsigned vblock = blockIdx.x;
+  if (a.ticket != nullptr) {
+    if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
+    __syncthreads();
+    vblock = s_vblock;
+  }
+  const long long idx = (long long)vblock * blockDim.x + threadIdx.x;
   if (idx >= (long long)a.n_work * a.M) return;
   const int w = (int)(idx / a.M);
   const int m = (int)(idx - (long long)w * a.M);
@@ -332,7 +363,7 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_oc, off_flux, total;
+  size_t off_po, off_pid, off_order, off_oc, off_ticket, off_progress, off_flux, total;
 };
 
 WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
@@ -342,6 +373,9 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
   L.off_pid = o;   o = align_up(o + sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
   L.off_order = o; o = align_up(o + sizeof(int) * (size_t)d.n_sc);
   L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
+  L.off_ticket = o; o = align_up(o + sizeof(int));
+  L.off_progress = o;
+  if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
   L.off_flux = o;
   if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
   L.total = o;
@@ -377,8 +411,7 @@ int pick_block(long long n_threads, int requested) {
   return 128;
 }
 
-// Shared launcher: level-major sweep over the reach DAG (each launch handles the sub-catchments of
-// one topological level for all members; a level only reads fluxes written by earlier launches).
+// Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.
 template <bool CAL>
 int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, const int32_t* po_host,
                   const int32_t* pid_host, char* ws, cudaStream_t st) {
@@ -390,12 +423,8 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   const WsLayout L = ws_layout(dims, E, CAL);
   std::vector<int> order;
   order.reserve(S);
-  std::vector<int> level_start(nl + 1, 0);
-  for (int l = 0; l < nl; ++l) {
-    level_start[l] = (int)order.size();
+  for (int l = 0; l < nl; ++l)
     for (int s = 0; s < S; ++s) if (lvl[s] == l) order.push_back(s);
-  }
-  level_start[nl] = (int)order.size();
 
   if (S > 1 || E > 0) {
     if (!ws) return fail(SIMPLYP_EINVAL, "workspace required for n_sc > 1%s");
@@ -413,19 +442,26 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   }
   if (CAL) a.flux = (S > 1) ? reinterpret_cast<double*>(ws + L.off_flux) : nullptr;
 
-  for (int l = 0; l < nl; ++l) {
-    const int n_work = level_start[l + 1] - level_start[l];
-    if (n_work == 0) continue;
-    a.n_work = n_work;
-    a.work_sc = (S > 1) ? reinterpret_cast<const int*>(ws + L.off_order) + level_start[l] : nullptr;
-    const long long n_threads = (long long)n_work * dims.n_members;
-    const int block = pick_block(n_threads, opt.threads_per_block);
-    const long long grid = (n_threads + block - 1) / block;
-    const size_t smem = (size_t)block * sizeof(Cold);
-    simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
-    g_launches.fetch_add(1);
-    SP_CUDA(cudaGetLastError());
+  // One launch for the whole network: threads are laid out level by level (all members of a reach are
+  // consecutive, so a warp holds one reach for 32 members whenever M >= 32) and advance as a wavefront.
+  a.n_work = S;
+  if (S > 1) {
+    a.work_sc = reinterpret_cast<const int*>(ws + L.off_order);
+    a.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
+    a.progress = reinterpret_cast<int*>(ws + L.off_progress);
+    SP_CUDA(cudaMemsetAsync(ws + L.off_ticket, 0, L.off_flux - L.off_ticket, st));
+  } else {
+    a.work_sc = nullptr;
+    a.ticket = nullptr;
+    a.progress = nullptr;
   }
+  const long long n_threads = (long long)S * dims.n_members;
+  const int block = pick_block(n_threads, opt.threads_per_block);
+  const long long grid = (n_threads + block - 1) / block;
+  const size_t smem = (size_t)block * sizeof(Cold);
+  simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+  g_launches.fetch_add(1);
+  SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;
 }
 

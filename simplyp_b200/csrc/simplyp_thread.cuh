@@ -27,10 +27,17 @@ struct ThreadCounters {
 };
 
 // IO policy concept:
+//   bool ready(int day);                         // non-blocking: are the inputs of `day` available yet?
 //   void forcing(int day, double& P, double& E, double& doy);
 //   void upstream(int day, double (&us)[4]);     // area-scaled Qr, Msus, TDP, PP of the parents, summed
 //   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
 //             const Cold& c);                    // y holds the raw end-of-day ODE states
+//   void publish(int day);                       // make `day`'s outputs visible to downstream reaches
+//
+// Reach routing (model.py:508-544) rides on ready()/publish(): a lane whose upstream reaches have not
+// finished the day it wants to start simply polls once per loop iteration while the other lanes of its
+// warp keep stepping, so upstream and downstream reaches advance as a day-skewed wavefront inside one
+// launch and nobody ever blocks a warp-mate.
 template <class IO>
 SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int nc_last,
                          const ThreadOptions& opt, int n_days, Cold& c, IO& io, ThreadCounters& cnt) {
@@ -38,30 +45,42 @@ SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int n
   Flags fl;
   RK rk;
   DayAux aux;
-  double y[NL], acc[NA], us[4];
+  double y[NL], acc[NA];
   double Kf;
   setup_thread(mp, sp, A_qr0, nc_last, opt.strict_quirks, opt.run_mode_cal, h, c, fl, y, Kf);
   cnt.steps = cnt.rejected = cnt.rhs_evals = 0;
   cnt.status = 0;
   if (n_days <= 0) return;
 
-  int day = 0;
-  double P, E, doy;
-  io.forcing(day, P, E, doy);
-  io.upstream(day, us);
-  begin_day(mp, sp, c, fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) acc[i] = 0.0;
-  rhs(h, y, rk.k1, rk.a1);
-  cnt.rhs_evals = 1;
-
   const double T = opt.step_len;
+  int day = 0;
   double t = 0.0;
   double hstep = 0.05 * T;   // first guess; the controller takes over after the first attempt
   int day_steps = 0;
   bool grow_ok = true;
+  bool begin = true;         // the current day has not been started yet
 
   while (true) {
+    if (begin) {
+      // ---- start of a day: pre-ODE algebra (:497-618) --------------------------------------
+      // (a lane that is not ready skips this iteration's step below and polls again next iteration;
+      //  it re-converges with its warp-mates at the loop back-edge, so it can never starve them)
+      if (io.ready(day)) {
+      double P, E, doy, us[4];
+      io.forcing(day, P, E, doy);
+      io.upstream(day, us);
+      begin_day(mp, sp, c, fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+      rhs(h, y, rk.k1, rk.a1);
+      cnt.rhs_evals += 1;
+      t = 0.0;
+      day_steps = 0;
+      hstep = sp_min(hstep, T);
+      begin = false;
+      }
+    }
+    if (!begin) {
     const double rem = T - t;
     const bool last = hstep * 1.0000001 >= rem;
     const double hh = last ? rem : hstep;
@@ -95,7 +114,7 @@ SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int n
     }
 
     if (accept && last) {
-      // ---- day boundary ------------------------------------------------------------------
+      // ---- end of a day: post-ODE algebra (:643-724), output ---------------------------------
       double non[13];
       double yraw[NL];
 #pragma unroll
@@ -106,19 +125,12 @@ SP_HD void run_member_sc(const double* mp, const double* sp, double A_qr0, int n
       for (int i = 0; i < NL; ++i) finite = finite && (yraw[i] - yraw[i] == 0.0);
       if (!finite) cnt.status |= 2;
       io.emit(day, yraw, io.wants_vr() ? reach_volume(h, yraw[iQr]) : 0.0, acc, non, c);
+      io.publish(day);
       ++day;
       if (day >= n_days) break;
-      io.forcing(day, P, E, doy);
-      io.upstream(day, us);
-      begin_day(mp, sp, c, fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);
-#pragma unroll
-      for (int i = 0; i < NA; ++i) acc[i] = 0.0;
-      rhs(h, y, rk.k1, rk.a1);
-      cnt.rhs_evals += 1;
-      t = 0.0;
-      day_steps = 0;
-      hstep = sp_min(hstep, T);
+      begin = true;
     }
+    }  // if (!begin)
   }
 }
 

@@ -33,6 +33,8 @@ struct HostIO {
     }
   }
   bool wants_vr() const { return true; }
+  bool ready(int) const { return true; }
+  void publish(int) const {}
   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
             const Cold&) const {
     double* row = out + (((size_t)m * S + s) * D + day) * SIMPLYP_NOUT;

@@ -167,6 +167,36 @@ def test_synthetic_network_vs_oracle(cabi):
         parity.assert_frames_close(TC[SC], R[SC], TCo[SC], Ro[SC], "synthetic SC %d" % SC)
 
 
+def test_network_ensemble_lanes_share_a_warp(cabi):
+    """5 members x 5 reaches = 25 threads in ONE warp, parents and children side by side: the routing
+    wavefront must neither deadlock nor depend on who shares a warp (each member alone gives the same bits)."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from tests.golden.networks import network5_inputs
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    p, p_LU, p_SC, p_struc = network5_inputs(p, p_LU, p_SC, p_struc)
+    pk.validate_land_use(p_SC, p["SC_list"])
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(5, seed=11)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met.iloc[:200])
+    out, dg = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert np.all(np.isfinite(out)) and not np.any(dg[..., 3])
+    for i in range(5):
+        out1, _ = cabi.run_host(forcing, member[i:i + 1], sc[i:i + 1], topo.parent_offsets, topo.parent_ids, opt)
+        assert np.array_equal(out1[0], out[i]), i
+    # calibration mode of the same network: statistics at the outlet equal those of the full-output series
+    obs5 = {5: obs[1]}
+    obs_m, desc, labels = pk.obs_arrays(obs5, topo, met.iloc[:200].index, ("Q", "TDP"))
+    st, _ = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+    A5 = sc[:, 4, pk.SC_INDEX["A_catch"]][:, None]
+    q = out[:, 4, :, 5] * A5 * 1000 / 86400
+    o = obs_m[0]
+    ok = ~np.isnan(o)
+    nse = 1 - ((o[ok] - q[:, ok]) ** 2).sum(axis=1) / ((o[ok] - o[ok].mean()) ** 2).sum()
+    assert np.allclose(nse, st[:, 0, 1], rtol=1e-10, atol=1e-10)
+
+
 def test_edge_cases(cabi):
     from simplyp_b200 import model as spm, packing as pk, tarland
     p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="n")
