@@ -14,7 +14,8 @@ import numpy as np
 from . import packing as pk
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsimplyp_b200.so")
+# SIMPLYP_B200_LIB lets a developer A/B-test another build of the same library (still CUDA-only).
+LIB_PATH = os.environ.get("SIMPLYP_B200_LIB") or os.path.join(_HERE, "lib", "libsimplyp_b200.so")
 
 EXPORTS = [
     "simplyp_abi_version", "simplyp_version", "simplyp_last_error", "simplyp_device_count",
