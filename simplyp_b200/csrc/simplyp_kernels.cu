@@ -70,17 +70,87 @@ enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
 // obs_const[V][8]
 enum { OC_N = 0, OC_MEAN, OC_SS, OC_MEAN_LOG, OC_SS_LOG, OC_SUM, OC_STD };
 
+// ------------------------------------------------------------------------------------------ K1a forcing ring
+// The daily forcing (32 B/day, shared by every member and sub-catchment) is staged per block in a ring of
+// FORC_SLOTS shared-memory tiles of FORC_TILE days each, filled by 1-D TMA bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes) that signal one mbarrier per slot.
+// There is no producer warp: threads walk through the days at their own pace, and the LAST thread of the
+// block to leave tile k re-arms the slot and issues the copy of tile k+FORC_SLOTS into it.  A thread that
+// runs ahead of the ring polls (mbarrier.test_wait) once per loop iteration instead of blocking, so the
+// slowest thread — which is always inside a resident tile — is never held up.
+constexpr int FORC_TILE = 128;    // days per tile (4 KB)
+constexpr int FORC_SLOTS = 4;     // ring depth (16 KB per block)
+
+struct ForcingRing {
+  double tiles[FORC_SLOTS][FORC_TILE * SIMPLYP_NF];
+  unsigned long long full[FORC_SLOTS];   // mbarriers
+  unsigned left[FORC_SLOTS];             // threads that have left the tile currently held by the slot
+  unsigned n_consumers;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_parity(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void tma_load_tile(ForcingRing* ring, int slot, const double* forcing, int tile, int n_days) {
+  const int d0 = tile * FORC_TILE;
+  const int nd = (n_days - d0) < FORC_TILE ? (n_days - d0) : FORC_TILE;
+  const unsigned bytes = (unsigned)nd * SIMPLYP_NF * sizeof(double);
+  const unsigned bar = smem_u32(&ring->full[slot]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the slot are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(&ring->tiles[slot][0])), "l"(forcing + (size_t)d0 * SIMPLYP_NF), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------ IO policies
 struct IOBase {
   const KArgs& a;
   int m, s;
   const double* scp_member;  // this member's [S][NP_SC] block
-  __device__ IOBase(const KArgs& a_, int m_, int s_)
-      : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC) {}
+  ForcingRing* ring;
+  int my_tile;               // tile this thread currently reads from (-1 before the first day)
+  __device__ IOBase(const KArgs& a_, int m_, int s_, ForcingRing* ring_)
+      : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC),
+        ring(ring_), my_tile(-1) {}
+
+  // forcing tile of `day` resident?  On a tile change the thread first leaves its old tile (once).
+  __device__ __forceinline__ bool forcing_ready(int day) {
+    const int q = day / FORC_TILE;
+    if (q != my_tile) {
+      if (my_tile >= 0 && my_tile == q - 1) {
+        const int slot = my_tile % FORC_SLOTS;
+        const unsigned before = atomicAdd(&ring->left[slot], 1u);
+        if (before + 1 == ring->n_consumers) {            // last one out refills the slot
+          ring->left[slot] = 0;
+          const int next = my_tile + FORC_SLOTS;
+          if (next * FORC_TILE < a.D) tma_load_tile(ring, slot, a.forcing, next, a.D);
+        }
+        my_tile = -2 - q;                                   // left the old tile, not yet inside tile q
+      }
+      if (!mbar_test_parity(&ring->full[q % FORC_SLOTS], (unsigned)(q / FORC_SLOTS) & 1u)) return false;
+      my_tile = q;
+    }
+    return true;
+  }
 
   // Routing wavefront: day `d` of this reach may start once every directly-upstream reach of the same
   // member has published day `d` (acquire load pairs with the release store in publish()).
-  __device__ __forceinline__ bool ready(int day) const {
+  __device__ __forceinline__ bool ready(int day) {
+    if (!forcing_ready(day)) return false;
     if (a.progress == nullptr) return true;
     const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
     for (int e = e0; e < e1; ++e) {
@@ -98,10 +168,10 @@ struct IOBase {
   }
 
   __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy) const {
-    const double2 f = __ldg(reinterpret_cast<const double2*>(a.forcing + (size_t)day * SIMPLYP_NF));
-    P = f.x;
-    E = f.y;
-    doy = __ldg(a.forcing + (size_t)day * SIMPLYP_NF + 2);
+    const double* f = &ring->tiles[(day / FORC_TILE) % FORC_SLOTS][(day % FORC_TILE) * SIMPLYP_NF];
+    P = f[0];
+    E = f[1];
+    doy = f[2];
   }
 };
 
@@ -149,7 +219,8 @@ struct RunIO : IOBase {
 // needs; observed days update the running sums of the fit statistics.
 struct CalIO : IOBase {
   double f_TDP;
-  __device__ CalIO(const KArgs& a_, int m_, int s_, double f_TDP_) : IOBase(a_, m_, s_), f_TDP(f_TDP_) {}
+  __device__ CalIO(const KArgs& a_, int m_, int s_, ForcingRing* ring_, double f_TDP_)
+      : IOBase(a_, m_, s_, ring_), f_TDP(f_TDP_) {}
 
   __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
     us[0] = us[1] = us[2] = us[3] = 0.0;
@@ -233,7 +304,7 @@ struct CalIO : IOBase {
 // ------------------------------------------------------------------------------------------ K1
 template <bool CAL>
 __global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
-  extern __shared__ double smem_cold[];
+  extern __shared__ __align__(16) double smem_cold[];
   // Networks: blocks take a ticket so that "lower index" means "dispatched earlier"; a reach only ever
   // waits for reaches of lower topological level, which sit at lower indices, so a waiting block can only
   // wait for blocks that are already running or finished (no deadlock even if the grid is not co-resident).
@@ -245,7 +316,21 @@ __global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
     vblock = s_vblock;
   }
   const long long idx = (long long)vblock * blockDim.x + threadIdx.x;
-  if (idx >= (long long)a.n_work * a.M) return;
+  const long long n_items = (long long)a.n_work * a.M;
+
+  // forcing ring: thread 0 initialises the mbarriers and starts the first FORC_SLOTS tile copies
+  ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)blockDim.x * (sizeof(Cold) / sizeof(double)));
+  if (threadIdx.x == 0) {
+    const long long first = (long long)vblock * blockDim.x;
+    const long long rest = n_items - first;
+    ring->n_consumers = (unsigned)(rest < (long long)blockDim.x ? (rest > 0 ? rest : 0) : blockDim.x);
+    for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < FORC_SLOTS; ++i)
+      if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
+  }
+  __syncthreads();
+  if (idx >= n_items) return;
   const int w = (int)(idx / a.M);
   const int m = (int)(idx - (long long)w * a.M);
   const int s = a.work_sc ? a.work_sc[w] : w;
@@ -262,11 +347,11 @@ __global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
 
   ThreadCounters cnt;
   if (CAL) {
-    CalIO io(a, m, s, mp[SIMPLYP_P_F_TDP]);
+    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
     run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
     io.finalise();
   } else {
-    RunIO io(a, m, s);
+    RunIO io(a, m, s, ring);
     run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
   }
   if (a.diag) {
@@ -458,7 +543,7 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   const long long n_threads = (long long)S * dims.n_members;
   const int block = pick_block(n_threads, opt.threads_per_block);
   const long long grid = (n_threads + block - 1) / block;
-  const size_t smem = (size_t)block * sizeof(Cold);
+  const size_t smem = (size_t)block * sizeof(Cold) + sizeof(ForcingRing);
   simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());

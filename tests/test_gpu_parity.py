@@ -197,6 +197,31 @@ def test_network_ensemble_lanes_share_a_warp(cabi):
     assert np.allclose(nse, st[:, 0, 1], rtol=1e-10, atol=1e-10)
 
 
+def test_long_record_wraps_the_forcing_ring(cabi):
+    """1,300 days = 11 forcing tiles through the 4-slot TMA ring (slots are re-armed and refilled), with
+    members of very different speed in one block; member 0 is checked against the oracle over the whole window."""
+    from oracle import simplyp_oracle as orc
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load("1995-01-01", "1998-07-23", dynamic="y")
+    assert len(met) == 1300
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(160, seed=21)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    out, dg = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert np.all(np.isfinite(out)) and not np.any(dg[..., 3])
+    spd = dg[:, 0, 0] / 1300.0
+    assert spd.max() / spd.min() > 2.0            # fast and slow members really share blocks
+    out1, _ = cabi.run_host(forcing, member[7:8], sc[7:8], topo.parent_offsets, topo.parent_ids, opt)
+    assert np.array_equal(out1[0], out[7])
+    p0, pLU0, pSC0 = ens.apply_member_to_pandas(samples, 0, p, p_LU, p_SC)
+    _TC, Ro, _Kf, _ = orc.run_simply_p(met, p_struc, p_SU, pLU0, pSC0, p0, dyn, rtol=1e-10, atol=1e-13, mxstep=50000)
+    _tc, r = spm.raw_to_frames(out[0, 0], met.index, float(sc[0, 0, 0]), p["Msoil_m2"], p["f_TDP"], "None", None)
+    for c in ("Q_cumecs", "SS_mgl", "TDP_mgl", "PP_mgl", "TP_mgl", "SRP_mgl"):
+        assert max_rel(r[c].to_numpy(), Ro[1][c].to_numpy()) <= 1e-5, c
+
+
 def test_edge_cases(cabi):
     from simplyp_b200 import model as spm, packing as pk, tarland
     p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="n")
