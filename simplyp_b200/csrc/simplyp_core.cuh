@@ -12,7 +12,7 @@
 //   rhs()             ode_f                       :58-187
 //   setup_thread()    run_simply_p, setup part    :318-335, :349, :377-463, :469
 //   begin_day()       run_simply_p, pre-ODE part  :497-501, :549-594, :600-611, :618
-//   dp5_attempt()     replaces scipy.integrate.odeint (LSODA), :640
+//   dp5_attempt()     one embedded RK5(4) step attempt; replaces scipy.integrate.odeint (LSODA), :640
 //   end_day()         run_simply_p, post-ODE part :643-724
 #pragma once
 
@@ -124,6 +124,22 @@ SP_HD double sp_rcp(double x) {
 #endif
 }
 
+// Polynomial coefficients live in constant memory on the device: a DFMA can take a constant-bank operand
+// directly, whereas a 64-bit literal costs two extra move instructions every time it is rematerialised
+// (and with ~250 live registers the compiler rematerialises all of them inside the step loop).
+#if defined(__CUDA_ARCH__)
+#define SP_CONST __constant__
+#else
+#define SP_CONST static const
+#endif
+SP_CONST double kExpC[16] = {
+    1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.0 / 6.0, 0.5, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 479001600.0, 0.0, 0.0};
+SP_CONST double kLogC[16] = {
+    1.0 / 3.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 19.0, 1.0 / 17.0,
+    1.0 / 21.0, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4142135623730951, 0.0, 0.0, 0.0};
+
 // ~7 significant digits: only for the error norm and the step-size factor
 SP_HD double sp_rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
@@ -138,22 +154,21 @@ SP_HD double sp_rcp_fast(double x) {
 // e^x for |x| < 700, no range check (the RHS arguments -mu*Vs, b_Q*ln Qr, k_M*ln Qr are far inside).
 SP_HD double sp_exp_core(double x) {
   // x = k ln2 + r, |r| <= ln2/2 ; e^r by its degree-12 Taylor polynomial (remainder < 2e-16)
-  const double kf = rint(x * 1.4426950408889634074);
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double kf = rint(x * kExpC[0]);
+  double r = fma(kf, kExpC[1], x);
+  r = fma(kf, kExpC[2], r);
   const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
   const double p01 = 1.0 + r;
-  const double p23 = fma(r, 1.0 / 6.0, 0.5);
-  const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-  const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-  const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-  const double pc = 1.0 / 479001600.0;
+  const double p23 = fma(r, kExpC[3], kExpC[4]);
+  const double p45 = fma(r, kExpC[5], kExpC[6]);
+  const double p67 = fma(r, kExpC[7], kExpC[8]);
+  const double p89 = fma(r, kExpC[9], kExpC[10]);
+  const double pab = fma(r, kExpC[11], kExpC[12]);
   const double q0 = fma(r2, p23, p01);          // terms 0..3
   const double q1 = fma(r2, p67, p45);          // terms 4..7  (times r^4)
   const double q2 = fma(r2, pab, p89);          // terms 8..11 (times r^8)
   const double lo = fma(r4, q1, q0);
-  const double hi = fma(r4, pc, q2);            // pc carries r^12 = r^8 * r^4
+  const double hi = fma(r4, kExpC[13], q2);     // 1/12! carries r^12 = r^8 * r^4
   const double p = fma(r8, hi, lo);
   // scale by 2^k through the exponent field
   return sp_ll2d(sp_d2ll(p) + ((long long)kf << 52));
@@ -169,22 +184,21 @@ SP_HD double sp_log(double x) {
   long long e = ((b >> 52) & 0x7ff) - 1023;
   b = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
   double m = sp_ll2d(b);
-  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  if (m > kLogC[12]) { m *= 0.5; e += 1; }
   const double f = (m - 1.0) * sp_rcp(m + 1.0);
   const double s = f * f, s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
   // 1 + s/3 + s^2/5 + ... + s^10/21
-  const double a01 = fma(s, 1.0 / 3.0, 1.0);
-  const double a23 = fma(s, 1.0 / 7.0, 1.0 / 5.0);
-  const double a45 = fma(s, 1.0 / 11.0, 1.0 / 9.0);
-  const double a67 = fma(s, 1.0 / 15.0, 1.0 / 13.0);
-  const double a89 = fma(s, 1.0 / 19.0, 1.0 / 17.0);
-  const double aa = 1.0 / 21.0;
+  const double a01 = fma(s, kLogC[0], 1.0);
+  const double a23 = fma(s, kLogC[1], kLogC[2]);
+  const double a45 = fma(s, kLogC[3], kLogC[4]);
+  const double a67 = fma(s, kLogC[5], kLogC[6]);
+  const double a89 = fma(s, kLogC[7], kLogC[8]);
   const double c0 = fma(s2, a23, a01);
   const double c1 = fma(s2, a67, a45);
-  const double c2 = fma(s2, aa, a89);
+  const double c2 = fma(s2, kLogC[9], a89);
   const double poly = fma(s8, c2, fma(s4, c1, c0));
   const double ed = (double)e;
-  return fma(ed, 6.93147180369123816490e-01, fma(2.0 * f, poly, ed * 1.90821492927058770002e-10));
+  return fma(ed, kLogC[10], fma(2.0 * f, poly, ed * kLogC[11]));
 }
 
 // f_x(x, thr, 0.01) expressed on u = (x-thr)/(thr*0.01): 0 for u<0, 1 for u>1, 3u^2-2u^3 between.
@@ -443,7 +457,8 @@ SP_HD void end_day(const Hot& h, Cold& c, const Flags& fl, int dynamic_epc0, con
 }
 
 // ------------------------------------------------------------------------------------------
-// Dormand–Prince 5(4) with FSAL.  The accumulators are pure quadratures (the RHS does not depend
+// Embedded explicit Runge-Kutta 5(4) with FSAL (Tsitouras' pair; -DSP_DOPRI5 selects Dormand-Prince).
+// The accumulators are pure quadratures (the RHS does not depend
 // on them), so their stage derivatives are folded into two running sums (5th-order weights and
 // error weights) instead of being stored per stage.
 struct RK {
@@ -452,62 +467,109 @@ struct RK {
 };
 
 namespace dp {
+#ifndef SP_DOPRI5
+// Tsitouras 5(4) (Ch. Tsitouras, Comput. Math. Appl. 62 (2011) 770-775): same 7-stage FSAL structure as
+// Dormand-Prince but smaller principal error coefficients -> fewer steps at equal accuracy.
+constexpr double a21 = 0.161;
+constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
+constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401,
+                 a65 = -0.028269050394068383;
+constexpr double b1 = 0.09646076681806523, b2 = 0.01, b3 = 0.4798896504144996, b4 = 1.379008574103742,
+                 b5 = -3.290069515436081, b6 = 2.324710524099774;
+constexpr double e1 = -0.00178001105222577714, e2 = -0.0008164344596567469, e3 = 0.007880878010261995,
+                 e4 = -0.1447110071732629, e5 = 0.5823571654525552, e6 = -0.45808210592918697, e7 = 0.015151515151515152;
+#else
+// Dormand-Prince 5(4)
 constexpr double a21 = 1.0 / 5.0;
 constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
 constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
 constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0, a54 = -212.0 / 729.0;
 constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0, a64 = 49.0 / 176.0,
                  a65 = -5103.0 / 18656.0;
-constexpr double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
-constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
+constexpr double b1 = 35.0 / 384.0, b2 = 0.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0, b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+constexpr double e1 = 71.0 / 57600.0, e2 = 0.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
                  e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+#endif
 }  // namespace dp
 
 // One step attempt of size hh from (y, acc).  On return ynew/accnew hold the 5th-order solution,
 // k7/a7 the derivative there, and the return value is the scaled RMS error (<= 1 accepts);
 // a non-finite error is returned as +inf.
+// Stage derivatives k2..k5 of the live states, parked between stages.  They stay in registers: a
+// shared-memory variant ([stage][state][thread] columns, 168 registers, 3 blocks/SM) was measured 8 % slower
+// at 1.6e5 members and 75 % slower at 1e4 members (spills + LDS latency on the critical path).
+struct RegStages {
+  double k[4][NL];
+  SP_HD double ld(int j, int i) const { return k[j][i]; }
+  SP_HD void st(int j, int i, double v) { k[j][i] = v; }
+};
+
+template <class KS>
 SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc)[NA], const RK& rk, double hh,
                          double rtol, double atol, double (&ynew)[NL], double (&accnew)[NA], double (&k7)[NL],
-                         double (&a7)[NA]) {
+                         double (&a7)[NA], KS& ks) {
   using namespace dp;
-  double k2[NL], k3[NL], k4[NL], k5[NL], k6[NL], yt[NL], da[NA];
+  double kk[NL], yt[NL], da[NA];
   double sb[NA], se[NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) { sb[i] = b1 * rk.a1[i]; se[i] = e1 * rk.a1[i]; }
 
+  // stage 2
 #pragma unroll
   for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a21 * rk.k1[i]);
-  rhs(c, yt, k2, da);  // b2 = e2 = 0: no accumulator contribution
+  rhs(c, yt, kk, da);
 #pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a31 * rk.k1[i] + a32 * k2[i]);
-  rhs(c, yt, k3, da);
+  for (int i = 0; i < NL; ++i) ks.st(0, i, kk[i]);
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { sb[i] += b2 * da[i]; se[i] += e2 * da[i]; }
+  // stage 3
+#pragma unroll
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a31 * rk.k1[i] + a32 * kk[i]);
+  rhs(c, yt, kk, da);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) ks.st(1, i, kk[i]);
 #pragma unroll
   for (int i = 0; i < NA; ++i) { sb[i] += b3 * da[i]; se[i] += e3 * da[i]; }
+  // stage 4
 #pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a41 * rk.k1[i] + a42 * k2[i] + a43 * k3[i]);
-  rhs(c, yt, k4, da);
+  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a41 * rk.k1[i] + a42 * ks.ld(0, i) + a43 * kk[i]);
+  rhs(c, yt, kk, da);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) ks.st(2, i, kk[i]);
 #pragma unroll
   for (int i = 0; i < NA; ++i) { sb[i] += b4 * da[i]; se[i] += e4 * da[i]; }
+  // stage 5
 #pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a51 * rk.k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
-  rhs(c, yt, k5, da);
+  for (int i = 0; i < NL; ++i)
+    yt[i] = y[i] + hh * (a51 * rk.k1[i] + a52 * ks.ld(0, i) + a53 * ks.ld(1, i) + a54 * kk[i]);
+  rhs(c, yt, kk, da);
+#pragma unroll
+  for (int i = 0; i < NL; ++i) ks.st(3, i, kk[i]);
 #pragma unroll
   for (int i = 0; i < NA; ++i) { sb[i] += b5 * da[i]; se[i] += e5 * da[i]; }
+  // stage 6
 #pragma unroll
   for (int i = 0; i < NL; ++i)
-    yt[i] = y[i] + hh * (a61 * rk.k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
-  rhs(c, yt, k6, da);
+    yt[i] = y[i] + hh * (a61 * rk.k1[i] + a62 * ks.ld(0, i) + a63 * ks.ld(1, i) + a64 * ks.ld(2, i) + a65 * kk[i]);
+  rhs(c, yt, kk, da);
 #pragma unroll
   for (int i = 0; i < NA; ++i) { sb[i] += b6 * da[i]; se[i] += e6 * da[i]; }
+  // 5th-order solution and the part of the error estimate that does not need k7 (kk holds k6)
+  double ee[NL];
 #pragma unroll
-  for (int i = 0; i < NL; ++i)
-    ynew[i] = y[i] + hh * (b1 * rk.k1[i] + b3 * k3[i] + b4 * k4[i] + b5 * k5[i] + b6 * k6[i]);
+  for (int i = 0; i < NL; ++i) {
+    const double k2 = ks.ld(0, i), k3 = ks.ld(1, i), k4 = ks.ld(2, i), k5 = ks.ld(3, i);
+    ynew[i] = y[i] + hh * (b1 * rk.k1[i] + b2 * k2 + b3 * k3 + b4 * k4 + b5 * k5 + b6 * kk[i]);
+    ee[i] = e1 * rk.k1[i] + e2 * k2 + e3 * k3 + e4 * k4 + e5 * k5 + e6 * kk[i];
+  }
   rhs(c, ynew, k7, a7);
 
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < NL; ++i) {
-    const double err = hh * (e1 * rk.k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k7[i]);
+    const double err = hh * (ee[i] + e7 * k7[i]);
     const double sc = atol + rtol * sp_max(fabs(y[i]), fabs(ynew[i]));
     const double q = err * sp_rcp_fast(sc);
     s += q * q;

@@ -303,7 +303,7 @@ struct CalIO : IOBase {
 
 // ------------------------------------------------------------------------------------------ K1
 template <bool CAL>
-__global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
+__global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   // Networks: blocks take a ticket so that "lower index" means "dispatched earlier"; a reach only ever
   // waits for reaches of lower topological level, which sit at lower indices, so a waiting block can only
@@ -346,13 +346,14 @@ __global__ void __launch_bounds__(128) simplyp_integrate_kernel(const KArgs a) {
   const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
 
   ThreadCounters cnt;
+  RegStages ks;
   if (CAL) {
     CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
-    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
+    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, ks, cnt);
     io.finalise();
   } else {
     RunIO io(a, m, s, ring);
-    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, cnt);
+    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, ks, cnt);
   }
   if (a.diag) {
     long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;

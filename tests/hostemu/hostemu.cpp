@@ -65,7 +65,8 @@ extern "C" int hostemu_run(const SimplypDims* dims, const SimplypOptions* opt, c
       HostIO io{forcing, scp, po, pid, out, S, D, m, s};
       Cold c;
       ThreadCounters cnt;
-      run_member_sc(mp, scp + (size_t)s * SIMPLYP_NP_SC, A_qr0, nc_last, t, D, c, io, cnt);
+      RegStages ks;
+      run_member_sc(mp, scp + (size_t)s * SIMPLYP_NP_SC, A_qr0, nc_last, t, D, c, io, ks, cnt);
       if (diag) {
         int64_t* dg = diag + ((size_t)m * S + s) * SIMPLYP_NDIAG;
         dg[0] = cnt.steps; dg[1] = cnt.rejected; dg[2] = cnt.rhs_evals; dg[3] = cnt.status;
