@@ -11,6 +11,7 @@ SRC = os.path.join(HERE, "hostemu.cpp")
 LIB = os.path.join(HERE, "libsimplyp_hostemu.so")
 DEPS = [SRC, os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_core.cuh"),
         os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_thread.cuh"),
+        os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_quad.cuh"),
         os.path.join(ROOT, "include", "simplyp_b200.h")]
 
 _lib = None
@@ -54,3 +55,17 @@ def run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt):
                     sc_params.ctypes.data_as(vp), po.ctypes.data_as(vp), pid.ctypes.data_as(vp),
                     out.ctypes.data_as(vp), diag.ctypes.data_as(vp))
     return out, diag
+
+
+def quad_rhs_check(member_row, sc_row, P, E, doy, us, y7, dynamic_epc0=1, dynamic_erod=1):
+    """Largest relative difference between the quad formulation's derivatives and rhs() at one state."""
+    lib = load()
+    lib.hostemu_quad_rhs_check.restype = C.c_double
+    lib.hostemu_quad_rhs_check.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_int]
+    mp = np.ascontiguousarray(member_row, dtype=np.float64)
+    sp = np.ascontiguousarray(sc_row, dtype=np.float64)
+    us = np.ascontiguousarray(us, dtype=np.float64)
+    y7 = np.ascontiguousarray(y7, dtype=np.float64)
+    return float(lib.hostemu_quad_rhs_check(mp.ctypes.data, sp.ctypes.data, P, E, doy, us.ctypes.data,
+                                            y7.ctypes.data, dynamic_epc0, dynamic_erod))

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../simplyp_b200/csrc/simplyp_thread.cuh"
+#include "../../simplyp_b200/csrc/simplyp_quad.cuh"
 
 using namespace simplyp;
 
@@ -74,4 +75,40 @@ extern "C" int hostemu_run(const SimplypDims* dims, const SimplypOptions* opt, c
     }
   }
   return 0;
+}
+
+
+// Check of the quad (4 lanes per member) formulation against the scalar rhs(): evaluates both at the same
+// state and returns the largest relative difference over the 11 derivatives.
+extern "C" double hostemu_quad_rhs_check(const double* mp, const double* sp, double P, double E, double doy,
+                                         const double* us4, const double* y7, int dynamic_epc0, int dynamic_erod) {
+  Hot h; Cold c; Flags fl; DayAux aux; double y0[NL], Kf;
+  setup_thread(mp, sp, sp[SIMPLYP_SC_A_CATCH], 0, 1, 1, h, c, fl, y0, Kf);
+  double us[4] = {us4[0], us4[1], us4[2], us4[3]};
+  begin_day(mp, sp, c, fl, dynamic_epc0, dynamic_erod, P, E, doy, us, h, aux);
+  double y[NL], dy[NL], da[NA];
+  for (int i = 0; i < NL; ++i) y[i] = y7[i];
+  rhs(h, y, dy, da);
+  QuadHost q;
+  double yA[4], yB[4], dA[4], dB[4], dacc[4];
+  for (int l = 0; l < 4; ++l) {
+    build_lane_coef(h, l, q.c[l]);
+    yA[l] = y[quad_slotA(l)];
+    yB[l] = quad_slotB(l) >= 0 ? y[quad_slotB(l)] : 0.0;
+  }
+  q.eval(yA, yB, dA, dB, dacc);
+  double worst = 0.0;
+  for (int l = 0; l < 4; ++l) {
+    const double refA = dy[quad_slotA(l)];
+    worst = fmax(worst, fabs(dA[l] - refA) / fmax(fabs(refA), 1e-300));
+    if (quad_slotB(l) >= 0) {
+      const double refB = dy[quad_slotB(l)];
+      worst = fmax(worst, fabs(dB[l] - refB) / fmax(fabs(refB), 1e-300));
+    } else {
+      worst = fmax(worst, fabs(dB[l]));
+    }
+    const double refc = da[quad_acc(l)];
+    worst = fmax(worst, fabs(dacc[l] - refc) / fmax(fabs(refc), 1e-300));
+  }
+  return worst;
 }
