@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--period", default="2004", choices=["2004", "full"])
     ap.add_argument("--rtol", type=float, default=None)
     ap.add_argument("--atol", type=float, default=None)
+    ap.add_argument("--lanes", type=int, default=0, choices=[0, 1, 4],
+                    help="lanes per (member, sub-catchment): 0/4 = quad kernel (default), 1 = one thread per item")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -206,7 +208,9 @@ def run_ours(args):
     M_total = M_local * world
     w = build_workload(args.period, M_total)
     lo, hi = ens.shard_bounds(M_total, world, rank)
-    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol)
+    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol,
+                           lanes_per_item=args.lanes)
+    kernel_name = "simplyp_integrate_kernel<true>" if args.lanes == 1 else "simplyp_quad_kernel<true>"
     eng = Engine(local_rank)
     S, D, V = w["topo"].n_sc, w["forcing"].shape[0], w["obs_m"].shape[0]
 
@@ -311,7 +315,7 @@ def run_ours(args):
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": (achieved_tf / fp64_peak) if fp64_peak else None, "traffic": None,
                          "peak_source": "simplyp_measure_fp64_peak (DFMA probe, this run); MEASURED_PEAKS.json has no FP64 figure",
-                         "kernel": "simplyp_integrate_kernel<true>", "kernel_ms": kernel_ms,
+                         "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_launch": flops_local,
                          "steps_per_member_day": n_steps / ((hi - lo) * S * D), "rejected_frac": n_rej / max(n_steps, 1.0),
                          "rhs_per_member_day": n_rhs / ((hi - lo) * S * D),

@@ -145,7 +145,7 @@ enum {
   SIMPLYP_DG_STEPS = 0,  /* accepted + rejected step attempts      */
   SIMPLYP_DG_REJECTED,   /* rejected attempts                      */
   SIMPLYP_DG_RHS,        /* right-hand-side evaluations            */
-  SIMPLYP_DG_STATUS,     /* bit 0: max steps/day hit, bit 1: non-finite state */
+  SIMPLYP_DG_STATUS,     /* bit 0: max steps/day hit, bit 1: non-finite state, bit 2: input wait timed out */
   SIMPLYP_NDIAG
 };
 
@@ -168,8 +168,10 @@ typedef struct SimplypOptions {
   int32_t run_mode_cal;      /* p_SU.run_mode == 'cal': Kf derived per SC (model.py:449-451) */
   int32_t sc_qr0;            /* 0-based index of p['SC_Qr0'] in the run order */
   int32_t strict_quirks;     /* 1: replicate the leaked NC_type of model.py:442,676 */
-  int32_t threads_per_block; /* 0 = library default */
-  int32_t reserved[5];
+  int32_t threads_per_block; /* 0 = library default (scalar kernel only) */
+  int32_t lanes_per_item;    /* lanes that integrate one (member, sub-catchment): 0 = default (4, the quad
+                                kernel), 4, or 1 (one thread per item, the round-1 kernel kept for A/B runs) */
+  int32_t reserved[4];
 } SimplypOptions;
 
 /* ---- entry points -------------------------------------------------------------------------- */

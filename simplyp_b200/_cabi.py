@@ -35,7 +35,8 @@ class SimplypOptions(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("step_len", C.c_double),
                 ("max_steps_per_day", C.c_int32), ("dynamic_epc0", C.c_int32),
                 ("dynamic_erodibility", C.c_int32), ("run_mode_cal", C.c_int32), ("sc_qr0", C.c_int32),
-                ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("lanes_per_item", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class SimplypError(RuntimeError):

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "simplyp_thread.cuh"
+#include "simplyp_quad.cuh"
 
 using namespace simplyp;
 
@@ -63,6 +64,12 @@ struct KArgs {
   double* flux;                 // cal, S>1: [M][S][D][4]
   int* progress;                // S>1: [M][S] days completed (release/acquire flags of the routing wavefront)
   int* ticket;                  // S>1: block ticket counter (virtual block order = dispatch order)
+  // quad kernel, S>1: items (reach, member) are laid out level by level, each level padded to a multiple of
+  // 8 items so that the 8 quads of a lock-step warp never depend on each other
+  const long long* level_item_off;  // [n_levels+1] padded cumulative item counts
+  const int* level_order_off;       // [n_levels+1] offsets into work_sc
+  int n_levels;
+  long long n_items_padded;
 };
 
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
@@ -123,9 +130,10 @@ struct IOBase {
   const double* scp_member;  // this member's [S][NP_SC] block
   ForcingRing* ring;
   int my_tile;               // tile this thread currently reads from (-1 before the first day)
+  int wait_status;           // status bits raised by wait()
   __device__ IOBase(const KArgs& a_, int m_, int s_, ForcingRing* ring_)
       : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC),
-        ring(ring_), my_tile(-1) {}
+        ring(ring_), my_tile(-1), wait_status(0) {}
 
   // forcing tile of `day` resident?  On a tile change the thread first leaves its old tile (once).
   __device__ __forceinline__ bool forcing_ready(int day) {
@@ -145,6 +153,60 @@ struct IOBase {
       my_tile = q;
     }
     return true;
+  }
+
+  // Warp-granular variant for the quad kernel (all lanes call it with the same `day`; the ring's consumers
+  // are the warps of the block and lane 0 does the bookkeeping).
+  __device__ __forceinline__ bool forcing_ready_warp(int day) {
+    const int q = day / FORC_TILE;
+    if (q != my_tile) {
+      if (my_tile >= 0 && my_tile == q - 1) {
+        __syncwarp();                                         // every lane is done reading the old tile
+        if ((threadIdx.x & 31) == 0) {
+          const int slot = my_tile % FORC_SLOTS;
+          const unsigned before = atomicAdd(&ring->left[slot], 1u);
+          if (before + 1 == ring->n_consumers) {
+            ring->left[slot] = 0;
+            const int next = my_tile + FORC_SLOTS;
+            if (next * FORC_TILE < a.D) tma_load_tile(ring, slot, a.forcing, next, a.D);
+          }
+        }
+        my_tile = -2 - q;
+      }
+      if (!mbar_test_parity(&ring->full[q % FORC_SLOTS], (unsigned)(q / FORC_SLOTS) & 1u)) return false;
+      my_tile = q;
+    }
+    return true;
+  }
+  // upstream reaches of this item have published `day`?
+  __device__ __forceinline__ bool upstream_ready(int day) const {
+    if (a.progress == nullptr) return true;
+    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int* flag = a.progress + (size_t)m * a.S + a.parent_ids[e];
+      int done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(flag) : "memory");
+      if (done <= day) return false;
+    }
+    return true;
+  }
+  // quad program: block (the whole warp) until forcing and upstream inputs of `day` exist
+  // A watchdog (about 4 s of SM clock) turns a wait that can never end (a bug, or a launch that violates the
+  // dispatch-order argument) into status bit 2 instead of a hung device.
+  __device__ __forceinline__ void wait(int day) {
+    const long long limit = 8000000000ll;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (ok && !forcing_ready_warp(day)) ok = (clock64() - t0) < limit;
+    if (a.progress != nullptr) {
+      unsigned ns = 32;
+      while (ok && !__all_sync(0xffffffffu, upstream_ready(day))) {
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
+        ok = __all_sync(0xffffffffu, (clock64() - t0) < limit);
+      }
+    }
+    if (!ok) wait_status |= 4;
   }
 
   // Routing wavefront: day `d` of this reach may start once every directly-upstream reach of the same
@@ -364,6 +426,88 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------ K1 (quad form)
+// One QUAD of lanes per (member, sub-catchment) item, 8 items per warp in day lock-step (simplyp_quad.cuh).
+// Shared memory: one QuadMem per quad, then the forcing ring.
+template <bool CAL>
+__global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
+  extern __shared__ __align__(16) double smem_cold[];
+  __shared__ unsigned s_vblock;
+  unsigned vblock = blockIdx.x;
+  if (a.ticket != nullptr) {
+    if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
+    __syncthreads();
+    vblock = s_vblock;
+  }
+  const int quads_per_block = blockDim.x >> 2;
+  QuadMem* qmem = reinterpret_cast<QuadMem*>(smem_cold);
+  ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)quads_per_block * (sizeof(QuadMem) / sizeof(double)));
+  if (threadIdx.x == 0) {
+    ring->n_consumers = blockDim.x >> 5;          // the warps of the block
+    for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < FORC_SLOTS; ++i)
+      if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
+  }
+  __syncthreads();
+
+  long long idx = (long long)vblock * quads_per_block + (threadIdx.x >> 2);
+  bool valid;
+  int w, m;
+  if (a.level_item_off == nullptr) {               // one sub-catchment: items are the members
+    valid = idx < a.M;
+    if (!valid) idx = a.M - 1;                     // padding quads shadow the last item and write nothing
+    w = 0;
+    m = (int)idx;
+  } else {
+    if (idx >= a.n_items_padded) idx = a.n_items_padded - 1;
+    int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.level_item_off[mid] <= idx) lo = mid; else hi = mid;
+    }
+    long long local = idx - a.level_item_off[lo];
+    const int o0 = a.level_order_off[lo];
+    const long long n_real = (long long)(a.level_order_off[lo + 1] - o0) * a.M;
+    valid = local < n_real;
+    if (!valid) local = n_real - 1;
+    const int wl = (int)(local / a.M);
+    w = o0 + wl;
+    m = (int)(local - (long long)wl * a.M);
+  }
+  const int s = a.work_sc ? a.work_sc[w] : w;
+
+  const double* mp = a.member_params + (size_t)m * SIMPLYP_NP_MEMBER;
+  const double* scp = a.sc_params + (size_t)(a.Msc > 1 ? m : 0) * a.S * SIMPLYP_NP_SC;
+  const double* sp = scp + (size_t)s * SIMPLYP_NP_SC;
+  const double A_qr0 = scp[(size_t)a.sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+  const double* spl = scp + (size_t)(a.S - 1) * SIMPLYP_NP_SC;
+  const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
+  const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
+
+  QuadDev q;
+  q.ql = threadIdx.x & 3;
+  QuadMem& qm = qmem[threadIdx.x >> 2];
+  ThreadCounters cnt;
+  if (CAL) {
+    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
+    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    if (valid && q.ql == 0) io.finalise();
+    cnt.status |= io.wait_status;
+  } else {
+    RunIO io(a, m, s, ring);
+    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    cnt.status |= io.wait_status;
+  }
+  if (a.diag && valid && q.ql == 0) {
+    long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
+    dg[SIMPLYP_DG_STEPS] = cnt.steps;
+    dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
+    dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
+    dg[SIMPLYP_DG_STATUS] = cnt.status;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ obs constants
 // One block per observed series: n, mean, sum of squares about the mean (plain and log), sum, std.
 __global__ void obs_const_kernel(const double* obs, int D, double* obs_const) {
@@ -449,7 +593,7 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_oc, off_ticket, off_progress, off_flux, total;
+  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_ticket, off_progress, off_flux, total;
 };
 
 WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
@@ -458,6 +602,8 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
   L.off_po = o;    o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
   L.off_pid = o;   o = align_up(o + sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
   L.off_order = o; o = align_up(o + sizeof(int) * (size_t)d.n_sc);
+  L.off_lvl_items = o; o = align_up(o + sizeof(long long) * ((size_t)d.n_sc + 1));   // at most n_sc levels
+  L.off_lvl_order = o; o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
   L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
   L.off_ticket = o; o = align_up(o + sizeof(int));
   L.off_progress = o;
@@ -477,6 +623,8 @@ int check_common(const SimplypDims* dims, const SimplypOptions* opt, const void*
   if (opt->sc_qr0 < 0 || opt->sc_qr0 >= dims->n_sc) return fail(SIMPLYP_EINVAL, "sc_qr0 out of range%s");
   if (!(opt->rtol > 0.0) || !(opt->atol >= 0.0) || !(opt->step_len > 0.0))
     return fail(SIMPLYP_EINVAL, "rtol/atol/step_len must be positive%s");
+  if (opt->lanes_per_item != 0 && opt->lanes_per_item != 1 && opt->lanes_per_item != 4)
+    return fail(SIMPLYP_EINVAL, "lanes_per_item must be 0 (default), 1 or 4%s");
   return SIMPLYP_OK;
 }
 
@@ -541,11 +689,37 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     a.ticket = nullptr;
     a.progress = nullptr;
   }
-  const long long n_threads = (long long)S * dims.n_members;
-  const int block = pick_block(n_threads, opt.threads_per_block);
-  const long long grid = (n_threads + block - 1) / block;
-  const size_t smem = (size_t)block * sizeof(Cold) + sizeof(ForcingRing);
-  simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+  const long long n_items = (long long)S * dims.n_members;
+  long long n_items_padded = ((long long)dims.n_members + 7) / 8 * 8;
+  if (S > 1 && opt.lanes_per_item != 1) {
+    std::vector<long long> lvl_items(nl + 1, 0);
+    std::vector<int> lvl_order(nl + 1, 0);
+    for (int s = 0; s < S; ++s) lvl_order[lvl[s] + 1] += 1;
+    for (int l = 0; l < nl; ++l) {
+      const long long n_real = (long long)lvl_order[l + 1] * dims.n_members;
+      lvl_order[l + 1] += lvl_order[l];
+      lvl_items[l + 1] = lvl_items[l] + (n_real + 7) / 8 * 8;
+    }
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_items, lvl_items.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, st));
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_order, lvl_order.data(), sizeof(int) * (nl + 1), cudaMemcpyHostToDevice, st));
+    a.level_item_off = reinterpret_cast<const long long*>(ws + L.off_lvl_items);
+    a.level_order_off = reinterpret_cast<const int*>(ws + L.off_lvl_order);
+    a.n_levels = nl;
+    n_items_padded = lvl_items[nl];
+  }
+  a.n_items_padded = n_items_padded;
+  if (opt.lanes_per_item == 1) {
+    const int block = pick_block(n_items, opt.threads_per_block);
+    const long long grid = (n_items + block - 1) / block;
+    const size_t smem = (size_t)block * sizeof(Cold) + sizeof(ForcingRing);
+    simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+  } else {
+    const int block = 128;
+    const int qpb = block / 4;
+    const long long grid = (n_items_padded + qpb - 1) / qpb;
+    const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
+    simplyp_quad_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+  }
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;

@@ -26,7 +26,11 @@ DEFAULT_ATOL = 1e-10
 
 
 def make_options(p_SU, p, dynamic_options, topology, step_len=1.0, rtol=None, atol=None,
-                 strict_reference_quirks=True, threads_per_block=0):
+                 strict_reference_quirks=True, threads_per_block=0, lanes_per_item=None):
+    """SimplypOptions for a run.  `lanes_per_item`: 4 = quad kernel (library default), 1 = one thread per
+    (member, sub-catchment); the environment variable SIMPLYP_LANES overrides the default for A/B runs."""
+    if lanes_per_item is None:
+        lanes_per_item = int(os.environ.get("SIMPLYP_LANES", "0"))
     sc_ids = topology.sc_ids
     qr0 = int(p["SC_Qr0"])
     if qr0 not in sc_ids:
@@ -41,6 +45,7 @@ def make_options(p_SU, p, dynamic_options, topology, step_len=1.0, rtol=None, at
         sc_qr0=sc_ids.index(qr0),
         strict_quirks=1 if strict_reference_quirks else 0,
         threads_per_block=int(threads_per_block),
+        lanes_per_item=int(lanes_per_item),
     )
 
 

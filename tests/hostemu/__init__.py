@@ -32,7 +32,12 @@ def load():
     return _lib
 
 
-def run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt):
+def run_quad(forcing, member_params, sc_params, parent_offsets, parent_ids, opt):
+    """The quad program (4 lanes per member) executed by the host build (tests only)."""
+    return run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, entry="hostemu_run_quad")
+
+
+def run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, entry="hostemu_run"):
     """Same contract as simplyp_b200._cabi.run_host, executed by the host build (tests only)."""
     from simplyp_b200 import _cabi, packing as pk
     lib = load()
@@ -51,7 +56,7 @@ def run(forcing, member_params, sc_params, parent_offsets, parent_ids, opt):
     out = np.zeros((M, S, D, pk.NOUT))
     diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
     vp = C.c_void_p
-    lib.hostemu_run(C.byref(dims), C.byref(opt), forcing.ctypes.data_as(vp), member_params.ctypes.data_as(vp),
+    getattr(lib, entry)(C.byref(dims), C.byref(opt), forcing.ctypes.data_as(vp), member_params.ctypes.data_as(vp),
                     sc_params.ctypes.data_as(vp), po.ctypes.data_as(vp), pid.ctypes.data_as(vp),
                     out.ctypes.data_as(vp), diag.ctypes.data_as(vp))
     return out, diag

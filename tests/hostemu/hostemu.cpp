@@ -35,6 +35,7 @@ struct HostIO {
   }
   bool wants_vr() const { return true; }
   bool ready(int) const { return true; }
+  void wait(int) const {}
   void publish(int) const {}
   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
             const Cold&) const {
@@ -78,8 +79,41 @@ extern "C" int hostemu_run(const SimplypDims* dims, const SimplypOptions* opt, c
 }
 
 
-// Check of the quad (4 lanes per member) formulation against the scalar rhs(): evaluates both at the same
-// state and returns the largest relative difference over the 11 derivatives.
+
+// The quad program (simplyp_quad.cuh) executed with the 4 lanes as the 4 elements of a struct.
+extern "C" int hostemu_run_quad(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                                const double* member_params, const double* sc_params, const int32_t* po,
+                                const int32_t* pid, double* out, int64_t* diag) {
+  const int M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
+  ThreadOptions t;
+  t.rtol = opt->rtol; t.atol = opt->atol; t.step_len = opt->step_len;
+  t.max_steps_per_day = opt->max_steps_per_day > 0 ? opt->max_steps_per_day : 5000;
+  t.dynamic_epc0 = opt->dynamic_epc0; t.dynamic_erod = opt->dynamic_erodibility;
+  t.run_mode_cal = opt->run_mode_cal; t.strict_quirks = opt->strict_quirks;
+  for (int m = 0; m < M; ++m) {
+    const double* mp = member_params + (size_t)m * SIMPLYP_NP_MEMBER;
+    const double* scp = sc_params + (size_t)(Msc > 1 ? m : 0) * S * SIMPLYP_NP_SC;
+    const double* spl = scp + (size_t)(S - 1) * SIMPLYP_NP_SC;
+    const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
+    const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
+    const double A_qr0 = scp[(size_t)opt->sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    for (int s = 0; s < S; ++s) {
+      HostIO io{forcing, scp, po, pid, out, S, D, m, s};
+      QuadHost4 q;
+      QuadMem qm;
+      ThreadCounters cnt;
+      run_quad(q, mp, scp + (size_t)s * SIMPLYP_NP_SC, A_qr0, nc_last, t, D, true, qm, io, cnt);
+      if (diag) {
+        int64_t* dg = diag + ((size_t)m * S + s) * SIMPLYP_NDIAG;
+        dg[0] = cnt.steps; dg[1] = cnt.rejected; dg[2] = cnt.rhs_evals; dg[3] = cnt.status;
+      }
+    }
+  }
+  return 0;
+}
+
+// The quad formulation of ode_f against the scalar rhs() at one state: returns the largest relative
+// difference over the 12 derivatives (dQr/dt and dVr/dt are recovered from du/dt and the quad's slot B).
 extern "C" double hostemu_quad_rhs_check(const double* mp, const double* sp, double P, double E, double doy,
                                          const double* us4, const double* y7, int dynamic_epc0, int dynamic_erod) {
   Hot h; Cold c; Flags fl; DayAux aux; double y0[NL], Kf;
@@ -89,26 +123,25 @@ extern "C" double hostemu_quad_rhs_check(const double* mp, const double* sp, dou
   double y[NL], dy[NL], da[NA];
   for (int i = 0; i < NL; ++i) y[i] = y7[i];
   rhs(h, y, dy, da);
-  QuadHost q;
-  double yA[4], yB[4], dA[4], dB[4], dacc[4];
-  for (int l = 0; l < 4; ++l) {
-    build_lane_coef(h, l, q.c[l]);
-    yA[l] = y[quad_slotA(l)];
-    yB[l] = quad_slotB(l) >= 0 ? y[quad_slotB(l)] : 0.0;
-  }
-  q.eval(yA, yB, dA, dB, dacc);
+  QuadHost4 q;
+  QuadCoef<QuadHost4> qc;
+  quad_static_coef(q, h, qc);
+  quad_daily_coef(q, h, qc);
+  const double Qr = y[iQr], Vr = reach_volume(h, Qr);
+  const V4 yA = q.pick(y[iVsA], y[iVsS], y[iVg], log(Qr));
+  const V4 yB = q.pick(y[iMsus], y[iTDPr], y[iPPr], Vr);
+  V4 dA, dB, dacc, e;
+  quad_rhs(q, qc, yA, yB, dA, dB, dacc, e);
+  const double got[12] = {dA.v[0], dA.v[1], dA.v[2], dA.v[3] * Qr, dB.v[0], dB.v[1], dB.v[2],
+                          dacc.v[3], dacc.v[0], dacc.v[1], dacc.v[2], dB.v[3]};
+  // ode_f's dVr/dt = net = dQr/dt / (kQ Qr^b_Q) (:127-131)
+  const double net = dy[iQr] / (h.kQ * exp(h.bQ * log(Qr)));
+  const double want[12] = {dy[iVsA], dy[iVsS], dy[iVg], dy[iQr], dy[iMsus], dy[iTDPr], dy[iPPr],
+                           da[0], da[1], da[2], da[3], net};
   double worst = 0.0;
-  for (int l = 0; l < 4; ++l) {
-    const double refA = dy[quad_slotA(l)];
-    worst = fmax(worst, fabs(dA[l] - refA) / fmax(fabs(refA), 1e-300));
-    if (quad_slotB(l) >= 0) {
-      const double refB = dy[quad_slotB(l)];
-      worst = fmax(worst, fabs(dB[l] - refB) / fmax(fabs(refB), 1e-300));
-    } else {
-      worst = fmax(worst, fabs(dB[l]));
-    }
-    const double refc = da[quad_acc(l)];
-    worst = fmax(worst, fabs(dacc[l] - refc) / fmax(fabs(refc), 1e-300));
+  for (int i = 0; i < 12; ++i) {
+    const double scale = fmax(fabs(want[i]), 1e-12 * (1.0 + fabs(y[i < NL ? i : 0])));
+    worst = fmax(worst, fabs(got[i] - want[i]) / scale);
   }
   return worst;
 }
