@@ -174,6 +174,40 @@ SP_HD double sp_exp_core(double x) {
   return sp_ll2d(sp_d2ll(p) + ((long long)kf << 52));
 }
 
+// Table-driven e^x for the quad kernel: x = (32 m + j) ln2/32 + r with |r| <= ln2/64, e^x = 2^m * 2^(j/32) * e^r.
+// The reduction uses the 1.5*2^52 trick (the integer lands in the low word of the sum: no FRND/F2I), e^r is a
+// degree-6 polynomial (remainder r^7/7! < 4e-18) and 2^(j/32) comes from a 32-entry table (`tab`: shared
+// memory on the device, kExp2Tab on the host).  |x| < 700, no range check.  Accuracy ~1.5 ulp.
+SP_CONST double kExpT[12] = {
+    46.16624130844683,      // 32/ln2
+    -0.02166084937925916,     // -ln2/32, high part (22 trailing zero bits: k*hi is exact for |k| < 2^22)
+    -1.3239129268154012e-11,  // -ln2/32, low part
+    6755399441055744.0,      // 1.5*2^52
+    0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 0.0, 0.0, 0.0};
+// 2^(j/32), j = 0..31, correctly rounded (generated with 60-digit decimal arithmetic)
+SP_CONST double kExp2Tab[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+SP_HD double sp_exp_tab(double x, const double* tab) {
+  const double t = fma(x, kExpT[0], kExpT[3]);
+  const double kf = t - kExpT[3];
+  const int ki = (int)(unsigned)(sp_d2ll(t) & 0xffffffffLL);      // two's-complement integer in the low word
+  double r = fma(kf, kExpT[1], x);
+  r = fma(kf, kExpT[2], r);
+  const double r2 = r * r;
+  const double c = fma(r2, kExpT[8], fma(r, kExpT[7], kExpT[6]));
+  const double b = fma(r, kExpT[5], kExpT[4]);
+  const double p = fma(r2, fma(r2, c, b), 1.0 + r);
+  const double v = p * tab[ki & 31];
+  return sp_ll2d(sp_d2ll(v) + ((long long)(ki >> 5) << 52));
+}
+
 // Range-checked variant for the once-a-day algebra: arguments are clamped to [-700, 700]
 // (e^-700 ~ 1e-304 stands in for an underflow to 0).
 SP_HD double sp_exp(double x) { return sp_exp_core(sp_min(sp_max(x, -700.0), 700.0)); }
@@ -202,8 +236,19 @@ SP_HD double sp_log(double x) {
 }
 
 // f_x(x, thr, 0.01) expressed on u = (x-thr)/(thr*0.01): 0 for u<0, 1 for u>1, 3u^2-2u^3 between.
+SP_HD double sp_clamp01(double u) {
+#if defined(__CUDA_ARCH__)
+  // decided on the high word with integer compares: no fp64-pipe DSETP and none of the NaN fix-ups the
+  // compiler attaches to the min/max idiom (u is finite here; a NaN passes through and the step is rejected)
+  const int hi = __double2hiint(u);
+  const double z = (hi < 0) ? 0.0 : u;
+  return (hi >= 0x3ff00000) ? 1.0 : z;
+#else
+  return sp_min(sp_max(u, 0.0), 1.0);
+#endif
+}
 SP_HD double gate(double u) {
-  u = sp_min(sp_max(u, 0.0), 1.0);
+  u = sp_clamp01(u);
   return u * u * (3.0 - 2.0 * u);
 }
 
@@ -494,6 +539,16 @@ constexpr double e1 = 71.0 / 57600.0, e2 = 0.0, e3 = -71.0 / 16695.0, e4 = 71.0 
 #endif
 }  // namespace dp
 
+// The same tableau as a constant-bank table: a DFMA/DMUL reads a c[bank][offset] operand directly, whereas a
+// 64-bit literal is rematerialised with two moves at every use (the quad kernel has no registers to park 34
+// constants in).
+enum { RA21 = 0, RA31, RA32, RA41, RA42, RA43, RA51, RA52, RA53, RA54, RA61, RA62, RA63, RA64, RA65,
+       RB1, RB2, RB3, RB4, RB5, RB6, RE1, RE2, RE3, RE4, RE5, RE6, RE7, RK_N };
+SP_CONST double kRK[RK_N] = {
+    dp::a21, dp::a31, dp::a32, dp::a41, dp::a42, dp::a43, dp::a51, dp::a52, dp::a53, dp::a54,
+    dp::a61, dp::a62, dp::a63, dp::a64, dp::a65, dp::b1, dp::b2, dp::b3, dp::b4, dp::b5, dp::b6,
+    dp::e1, dp::e2, dp::e3, dp::e4, dp::e5, dp::e6, dp::e7};
+
 // One step attempt of size hh from (y, acc).  On return ynew/accnew hold the 5th-order solution,
 // k7/a7 the derivative there, and the return value is the scaled RMS error (<= 1 accepts);
 // a non-finite error is returned as +inf.
@@ -594,6 +649,18 @@ SP_HD double step_factor(double en) {
   const double f = 0.9 * (double)exp2f(-0.2f * __log2f((float)en));
 #else
   const double f = 0.9 * exp(-0.2 * log(en));
+#endif
+  return sp_min(5.0, sp_max(0.2, f));
+}
+
+// The same controller on the MEAN SQUARE of the scaled error (no square root): 0.9*(en^2)^(-1/10).
+SP_HD double step_factor_sq(double en2) {
+  if (!(en2 > 1e-60)) return 5.0;
+  if (!(en2 < 1e60)) return 0.2;
+#if defined(__CUDA_ARCH__)
+  const double f = 0.9 * (double)exp2f(-0.1f * __log2f((float)en2));
+#else
+  const double f = 0.9 * exp(-0.1 * log(en2));
 #endif
   return sp_min(5.0, sp_max(0.2, f));
 }

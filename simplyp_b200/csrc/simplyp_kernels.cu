@@ -433,6 +433,8 @@ template <bool CAL>
 __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ unsigned s_vblock;
+  __shared__ double s_exp2tab[32];
+  if (threadIdx.x < 32) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
   unsigned vblock = blockIdx.x;
   if (a.ticket != nullptr) {
     if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
@@ -487,6 +489,7 @@ __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
 
   QuadDev q;
   q.ql = threadIdx.x & 3;
+  q.tab = s_exp2tab;
   QuadMem& qm = qmem[threadIdx.x >> 2];
   ThreadCounters cnt;
   if (CAL) {

@@ -55,14 +55,13 @@ inline V4 v4_splat(double x) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = x; ret
 
 // elementary operations on T (double on the device, V4 in the host harness)
 SP_HD double qfma(double a, double b, double c) { return fma(a, b, c); }
-SP_HD double qexp(double x) { return sp_exp_core(x); }
 SP_HD double qgate(double u) { return gate(u); }
 SP_HD double qrcp(double x) { return sp_rcp(x); }
 SP_HD double qrcp_fast(double x) { return sp_rcp_fast(x); }
 SP_HD double qabs(double x) { return fabs(x); }
 SP_HD double qmax(double a, double b) { return sp_max(a, b); }
 #define SP_V4_MAP1(name, f) inline V4 name(const V4& a) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = f(a.v[l]); return r; }
-SP_V4_MAP1(qexp, sp_exp_core) SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
+SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
 SP_V4_MAP1(qabs, fabs)
 #undef SP_V4_MAP1
 inline V4 qmax(const V4& a, const V4& b) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = sp_max(a.v[l], b.v[l]); return r; }
@@ -77,6 +76,7 @@ struct QuadHost4 {
   using T = V4;
   T pick(double a, double b, double c, double d) const { return V4{{a, b, c, d}}; }
   T splat(double x) const { return v4_splat(x); }
+  T exp(const T& x) const { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = sp_exp_tab(x.v[l], kExp2Tab); return r; }
   T bcast(const T& x, int src) const { return v4_splat(x.v[src]); }
   T sum(const T& x) const { return v4_splat((x.v[0] + x.v[1]) + (x.v[2] + x.v[3])); }   // butterfly order
   double first(const T& x) const { return x.v[0]; }                                  // quad-uniform values only
@@ -89,12 +89,19 @@ struct QuadHost4 {
 #if defined(__CUDACC__)
 struct QuadDev {
   using T = double;
-  int ql;   // lane within the quad
+  int ql;              // lane within the quad
+  const double* tab;   // 2^(j/32) table in shared memory
+  __device__ __forceinline__ T exp(T x) const { return sp_exp_tab(x, tab); }
   __device__ __forceinline__ T pick(double a, double b, double c, double d) const {
     return ql == 0 ? a : (ql == 1 ? b : (ql == 2 ? c : d));
   }
   __device__ __forceinline__ T splat(double x) const { return x; }
-  __device__ __forceinline__ T bcast(T x, int src) const { return __shfl_sync(0xffffffffu, x, src, 4); }
+  __device__ __forceinline__ T bcast(T x, int src) const {
+    // the two halves are shuffled as ints: __shfl_sync(double) makes ptxas swap the register pair afterwards
+    const int lo = __shfl_sync(0xffffffffu, __double2loint(x), src, 4);
+    const int hi = __shfl_sync(0xffffffffu, __double2hiint(x), src, 4);
+    return __hiloint2double(hi, lo);
+  }
   __device__ __forceinline__ T sum(T x) const {
     x += __shfl_xor_sync(0xffffffffu, x, 1);
     x += __shfl_xor_sync(0xffffffffu, x, 2);
@@ -114,10 +121,10 @@ struct QuadCoef {
   using T = typename Q::T;
   T eY, eU;                    // own exponential: exp(eY*yA + eU*u)
   T p1, p0, g0, g1;            // own gate: w = p1*yA + p0 ; G = g0 + f(w)*w*g1   (f = smoothstep on [0,1])
-  T a0, aE, aSA, aSS, aG, aR;  // slot A: L = a0 + aE*e + aSA*QsA + aSS*QsS + aG*Qg + aR*Qr ; lane 3: dA = L*mA/Vr
-  T mA;
-  T b0, bK, bSA, bSS, bG;      // slot B: dB = b0 + bK*Qr^k + bSA*QsA + bSS*QsS + bG*Qg - yB*Qr/Vr ; lane 3: dB = L
-};
+  T a0, aE, aSA, aSS, aG, aR;  // slot A: L = a0 + aE*e + aSA*QsA + aSS*QsS + aG*Qg + aR*Qr ; dA = L*(m0 + mA/Vr)
+  T m0, mA;                    //   lanes 0-2: (1, 0) ; lane 3: (0, 1/(1-b_Q))  -> du/dt = net/((1-b_Q) Vr)
+  T b0, bK, bSA, bSS, bG;      // slot B: dB = b0 + bK*Qr^k + bSA*QsA + bSS*QsS + bG*Qg - yB*Qr/Vr
+};                             //   lane 3 (yB = Vr): yB*Qr/Vr = Qr, so its b-coefficients spell net + Qr (:127,131)
 
 // Coefficients that do not change from day to day (member constants), from the scalar program's Hot.
 template <class Q>
@@ -136,8 +143,9 @@ SP_HD void quad_static_coef(const Q& q, const Hot& h, QuadCoef<Q>& c) {
   c.aSS = q.pick(0.0, -1.0, h.beta * h.fS, omb * h.fS);
   c.aG = q.pick(0.0, 0.0, -1.0, 1.0);
   c.aR = q.pick(0.0, 0.0, 0.0, -1.0);
+  c.m0 = q.pick(1.0, 1.0, 1.0, 0.0);
   c.mA = q.pick(0.0, 0.0, 0.0, 1.0 / (1.0 - h.bQ));
-  c.bG = q.pick(0.0, h.tG, 0.0, 0.0);                            // :163
+  c.bG = q.pick(0.0, h.tG, 0.0, 1.0);                            // :163 ; lane 3: +Qg
   c.a0 = c.aE = c.b0 = c.bK = c.bSA = c.bSS = q.splat(0.0);
 }
 
@@ -146,10 +154,11 @@ template <class Q>
 SP_HD void quad_daily_coef(const Q& q, const Hot& h, QuadCoef<Q>& c) {
   c.a0 = q.pick(h.Pin - h.aE, h.Pin - h.aE, 0.0, h.qin0);        // :106,110 ; :127
   c.aE = q.pick(h.aE, h.aE, 0.0, 0.0);
-  c.b0 = q.pick(h.MsusUS, h.t0, h.PPUS, 0.0);                    // :144, :165-166, :177
+  const double omb = 1.0 - h.beta;
+  c.b0 = q.pick(h.MsusUS, h.t0, h.PPUS, h.qin0);                 // :144, :165-166, :177 ; lane 3: :127
   c.bK = q.pick(h.cM, 0.0, h.cP, 0.0);                           // :138-143, :171-176
-  c.bSA = q.pick(0.0, h.tA, 0.0, 0.0);                           // :154-161
-  c.bSS = q.pick(0.0, h.tS, 0.0, 0.0);
+  c.bSA = q.pick(0.0, h.tA, 0.0, omb * h.fA);                    // :154-161
+  c.bSS = q.pick(0.0, h.tS, 0.0, omb * h.fS);
 }
 
 // One evaluation of ode_f by the quad.  `e` returns the lane's own exponential (lane 3: Qr at this state).
@@ -159,7 +168,7 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   using T = typename Q::T;
   const T u = q.bcast(yA, 3);
   const T rV = qrcp(q.bcast(yB, 3));
-  e = qexp(qfma(c.eY, yA, c.eU * u));
+  e = q.exp(qfma(c.eY, yA, c.eU * u));
   const T w = qfma(c.p1, yA, c.p0);
   const T G = qfma(qgate(w) * w, c.g1, c.g0);
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
@@ -168,9 +177,9 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   const T r = Qr * rV;                       // Qr/Vr
   const T out = yB * r;                      // outflow of the lane's in-stream mass (:145,147,166,168,178,180)
   const T src = qfma(c.bK, qk, c.b0) + qfma(c.bSA, QsA, qfma(c.bSS, QsS, c.bG * Qg));
-  dA = q.sel3(L * (rV * c.mA), L);           // lane 3: du/dt = net/((1-b_Q) Vr)
-  dB = q.sel3(L, src - out);                 // lane 3: dVr/dt = net (:131)
-  dacc = q.sel3(Qr, out);                    // lane 3: dQr_av/dt = Qr (:132)
+  dA = L * qfma(rV, c.mA, c.m0);             // lane 3: du/dt = net/((1-b_Q) Vr)
+  dB = src - out;                            // lane 3: out = Vr*Qr/Vr = Qr, src = net + Qr -> dVr/dt = net (:131)
+  dacc = out;                                // lane 3: dQr_av/dt = Qr (:132)
 }
 
 // Per-lane Runge-Kutta state.
@@ -182,35 +191,35 @@ struct QuadState {
   T e1;                 // own exponential at the current point (lane 3: Qr)
 };
 
-// One embedded RK5(4) step attempt of the quad.  Returns the scaled RMS error of the member (same on all lanes).
+// One embedded RK5(4) step attempt of the quad.  Returns the MEAN SQUARE of the scaled error over the 12
+// components (same on all lanes); <= 1 accepts.
 template <class Q>
 SP_HD double quad_attempt(const Q& q, const QuadCoef<Q>& c, const QuadState<Q>& s, double hh, double rtol, double atol,
                           typename Q::T& ynA, typename Q::T& ynB, typename Q::T& accn, typename Q::T& k7A,
                           typename Q::T& k7B, typename Q::T& a7, typename Q::T& e7o) {
-  using namespace dp;
   using T = typename Q::T;
   T kA2, kA3, kA4, kA5, kA6, kB2, kB3, kB4, kB5, kB6, da, ee;
-  T sb = b1 * s.a1, se = e1 * s.a1;
-  quad_rhs(q, c, qfma(hh, a21 * s.k1A, s.yA), qfma(hh, a21 * s.k1B, s.yB), kA2, kB2, da, ee);
-  sb = qfma(b2, da, sb); se = qfma(e2, da, se);
-  quad_rhs(q, c, qfma(hh, qfma(a32, kA2, a31 * s.k1A), s.yA), qfma(hh, qfma(a32, kB2, a31 * s.k1B), s.yB), kA3, kB3, da, ee);
-  sb = qfma(b3, da, sb); se = qfma(e3, da, se);
-  quad_rhs(q, c, qfma(hh, qfma(a43, kA3, qfma(a42, kA2, a41 * s.k1A)), s.yA),
-           qfma(hh, qfma(a43, kB3, qfma(a42, kB2, a41 * s.k1B)), s.yB), kA4, kB4, da, ee);
-  sb = qfma(b4, da, sb); se = qfma(e4, da, se);
-  quad_rhs(q, c, qfma(hh, qfma(a54, kA4, qfma(a53, kA3, qfma(a52, kA2, a51 * s.k1A))), s.yA),
-           qfma(hh, qfma(a54, kB4, qfma(a53, kB3, qfma(a52, kB2, a51 * s.k1B))), s.yB), kA5, kB5, da, ee);
-  sb = qfma(b5, da, sb); se = qfma(e5, da, se);
-  quad_rhs(q, c, qfma(hh, qfma(a65, kA5, qfma(a64, kA4, qfma(a63, kA3, qfma(a62, kA2, a61 * s.k1A)))), s.yA),
-           qfma(hh, qfma(a65, kB5, qfma(a64, kB4, qfma(a63, kB3, qfma(a62, kB2, a61 * s.k1B)))), s.yB), kA6, kB6, da, ee);
-  sb = qfma(b6, da, sb); se = qfma(e6, da, se);
-  ynA = qfma(hh, qfma(b6, kA6, qfma(b5, kA5, qfma(b4, kA4, qfma(b3, kA3, qfma(b2, kA2, b1 * s.k1A))))), s.yA);
-  ynB = qfma(hh, qfma(b6, kB6, qfma(b5, kB5, qfma(b4, kB4, qfma(b3, kB3, qfma(b2, kB2, b1 * s.k1B))))), s.yB);
+  T sb = kRK[RB1] * s.a1, se = kRK[RE1] * s.a1;
+  quad_rhs(q, c, qfma(hh, kRK[RA21] * s.k1A, s.yA), qfma(hh, kRK[RA21] * s.k1B, s.yB), kA2, kB2, da, ee);
+  sb = qfma(kRK[RB2], da, sb); se = qfma(kRK[RE2], da, se);
+  quad_rhs(q, c, qfma(hh, qfma(kRK[RA32], kA2, kRK[RA31] * s.k1A), s.yA), qfma(hh, qfma(kRK[RA32], kB2, kRK[RA31] * s.k1B), s.yB), kA3, kB3, da, ee);
+  sb = qfma(kRK[RB3], da, sb); se = qfma(kRK[RE3], da, se);
+  quad_rhs(q, c, qfma(hh, qfma(kRK[RA43], kA3, qfma(kRK[RA42], kA2, kRK[RA41] * s.k1A)), s.yA),
+           qfma(hh, qfma(kRK[RA43], kB3, qfma(kRK[RA42], kB2, kRK[RA41] * s.k1B)), s.yB), kA4, kB4, da, ee);
+  sb = qfma(kRK[RB4], da, sb); se = qfma(kRK[RE4], da, se);
+  quad_rhs(q, c, qfma(hh, qfma(kRK[RA54], kA4, qfma(kRK[RA53], kA3, qfma(kRK[RA52], kA2, kRK[RA51] * s.k1A))), s.yA),
+           qfma(hh, qfma(kRK[RA54], kB4, qfma(kRK[RA53], kB3, qfma(kRK[RA52], kB2, kRK[RA51] * s.k1B))), s.yB), kA5, kB5, da, ee);
+  sb = qfma(kRK[RB5], da, sb); se = qfma(kRK[RE5], da, se);
+  quad_rhs(q, c, qfma(hh, qfma(kRK[RA65], kA5, qfma(kRK[RA64], kA4, qfma(kRK[RA63], kA3, qfma(kRK[RA62], kA2, kRK[RA61] * s.k1A)))), s.yA),
+           qfma(hh, qfma(kRK[RA65], kB5, qfma(kRK[RA64], kB4, qfma(kRK[RA63], kB3, qfma(kRK[RA62], kB2, kRK[RA61] * s.k1B)))), s.yB), kA6, kB6, da, ee);
+  sb = qfma(kRK[RB6], da, sb); se = qfma(kRK[RE6], da, se);
+  ynA = qfma(hh, qfma(kRK[RB6], kA6, qfma(kRK[RB5], kA5, qfma(kRK[RB4], kA4, qfma(kRK[RB3], kA3, qfma(kRK[RB2], kA2, kRK[RB1] * s.k1A))))), s.yA);
+  ynB = qfma(hh, qfma(kRK[RB6], kB6, qfma(kRK[RB5], kB5, qfma(kRK[RB4], kB4, qfma(kRK[RB3], kB3, qfma(kRK[RB2], kB2, kRK[RB1] * s.k1B))))), s.yB);
   quad_rhs(q, c, ynA, ynB, k7A, k7B, a7, e7o);
   accn = qfma(hh, sb, s.acc);
-  const T eA = hh * qfma(e7, k7A, qfma(e6, kA6, qfma(e5, kA5, qfma(e4, kA4, qfma(e3, kA3, qfma(e2, kA2, e1 * s.k1A))))));
-  const T eB = hh * qfma(e7, k7B, qfma(e6, kB6, qfma(e5, kB5, qfma(e4, kB4, qfma(e3, kB3, qfma(e2, kB2, e1 * s.k1B))))));
-  const T ec = hh * qfma(e7, a7, se);
+  const T eA = hh * qfma(kRK[RE7], k7A, qfma(kRK[RE6], kA6, qfma(kRK[RE5], kA5, qfma(kRK[RE4], kA4, qfma(kRK[RE3], kA3, qfma(kRK[RE2], kA2, kRK[RE1] * s.k1A))))));
+  const T eB = hh * qfma(kRK[RE7], k7B, qfma(kRK[RE6], kB6, qfma(kRK[RE5], kB5, qfma(kRK[RE4], kB4, qfma(kRK[RE3], kB3, qfma(kRK[RE2], kB2, kRK[RE1] * s.k1B))))));
+  const T ec = hh * qfma(kRK[RE7], a7, se);
   // error weights (odeint: atol + rtol*|y|).  Lane 3's slot A is u = ln Qr: err_Qr = Qr err_u, scale on Qr.
   const T Qmax = qmax(s.e1, e7o);
   const T sA = q.sel3(Qmax, qmax(qabs(s.yA), qabs(ynA)));
@@ -218,9 +227,8 @@ SP_HD double quad_attempt(const Q& q, const QuadCoef<Q>& c, const QuadState<Q>& 
   const T qA = (eA * wA) * qrcp_fast(qfma(rtol, sA, atol));
   const T qB = eB * qrcp_fast(qfma(rtol, qmax(qabs(s.yB), qabs(ynB)), atol));
   const T qc = ec * qrcp_fast(qfma(rtol, qmax(qabs(s.acc), qabs(accn)), atol));
-  const double sum = q.first(q.sum(qfma(qA, qA, qfma(qB, qB, qc * qc))));
-  const double en = sqrt(sum * (1.0 / 12.0));
-  return (en == en) ? en : INFINITY;   // NaN -> reject
+  const double en2 = q.first(q.sum(qfma(qA, qA, qfma(qB, qB, qc * qc)))) * (1.0 / 12.0);
+  return (en2 == en2) ? en2 : INFINITY;   // NaN -> reject
 }
 
 // Day-boundary state of a quad kept outside the registers (device: shared memory, one per quad).
@@ -293,16 +301,16 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       const bool last = hstep * 1.0000001 >= rem;
       const double hh = active ? (last ? rem : hstep) : hstep;
       T ynA, ynB, accn, k7A, k7B, a7, e7;
-      const double en = quad_attempt(q, qc, s, hh, opt.rtol, opt.atol, ynA, ynB, accn, k7A, k7B, a7, e7);
+      const double en2 = quad_attempt(q, qc, s, hh, opt.rtol, opt.atol, ynA, ynB, accn, k7A, k7B, a7, e7);
       if (active) {
         n_steps += 1;
         day_steps += 1;
-        bool accept = en <= 1.0;
+        bool accept = en2 <= 1.0;
         if (!accept && (day_steps >= opt.max_steps_per_day || hh < 1e-12 * T1)) {
           accept = true;                          // forward-progress guard
           status |= 1;
         }
-        double fac = step_factor(en);
+        double fac = step_factor_sq(en2);
         if (accept) {
           t += hh;
           s.yA = ynA; s.yB = ynB; s.acc = accn;
