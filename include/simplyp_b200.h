@@ -171,7 +171,9 @@ typedef struct SimplypOptions {
   int32_t threads_per_block; /* 0 = library default (scalar kernel only) */
   int32_t lanes_per_item;    /* lanes that integrate one (member, sub-catchment): 0 = default (4, the quad
                                 kernel), 4, or 1 (one thread per item, the round-1 kernel kept for A/B runs) */
-  int32_t reserved[4];
+  int32_t pilot_days;        /* ensembles of one sub-catchment: days of the pilot run whose step counts order the
+                                members over the lock-step warps (0 = default 8, < 0 = no pilot) */
+  int32_t reserved[3];
 } SimplypOptions;
 
 /* ---- entry points -------------------------------------------------------------------------- */

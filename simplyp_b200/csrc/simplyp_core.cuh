@@ -653,16 +653,23 @@ SP_HD double step_factor(double en) {
   return sp_min(5.0, sp_max(0.2, f));
 }
 
-// The same controller on the MEAN SQUARE of the scaled error (no square root): 0.9*(en^2)^(-1/10).
+// The same controller on the MEAN SQUARE of the scaled error (no square root): 0.9*(en^2)^(-1/10) in [0.2, 5].
+// Device: fp32 lg2/ex2 with flush-to-zero and no range branches — an underflowing en^2 gives lg2 = -inf, hence
+// +inf, clamped to 5; an overflowing one gives 0, clamped to 0.2 (en^2 is never NaN here).
 SP_HD double step_factor_sq(double en2) {
-  if (!(en2 > 1e-60)) return 5.0;
-  if (!(en2 < 1e60)) return 0.2;
 #if defined(__CUDA_ARCH__)
-  const double f = 0.9 * (double)exp2f(-0.1f * __log2f((float)en2));
+  float l, f;
+  const float x = __double2float_rn(en2);
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  l *= -0.1f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(l));
+  return (double)fminf(fmaxf(0.9f * f, 0.2f), 5.0f);
 #else
+  if (!(en2 > 1e-38)) return 5.0;
+  if (!(en2 < 1e38)) return 0.2;
   const double f = 0.9 * exp(-0.1 * log(en2));
-#endif
   return sp_min(5.0, sp_max(0.2, f));
+#endif
 }
 
 }  // namespace simplyp

@@ -70,7 +70,13 @@ struct KArgs {
   const int* level_order_off;       // [n_levels+1] offsets into work_sc
   int n_levels;
   long long n_items_padded;
+  // cost ordering of an ensemble (quad kernel, one sub-catchment): a short pilot run counts the step attempts
+  // of every member; members are then dealt to the lock-step warps heaviest first
+  const int* perm;              // [M] member handled by item idx, or null
+  unsigned* cost;               // pilot: [M] step attempts
+  unsigned* hist;               // pilot: [COST_BUCKETS] histogram of the costs
 };
+constexpr int COST_BUCKETS = 4096;
 
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
 enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
@@ -363,6 +369,15 @@ struct CalIO : IOBase {
   }
 };
 
+// Pilot run: integrates, writes nothing per day.
+struct PilotIO : IOBase {
+  using IOBase::IOBase;
+  __device__ __forceinline__ void upstream(int, double (&us)[4]) const { us[0] = us[1] = us[2] = us[3] = 0.0; }
+  __device__ __forceinline__ bool wants_vr() const { return false; }
+  __device__ __forceinline__ void emit(int, const double (&)[NL], double, const double (&)[NA], const double (&)[13],
+                                       const Cold&) const {}
+};
+
 // ------------------------------------------------------------------------------------------ K1
 template <bool CAL>
 __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a) {
@@ -429,7 +444,8 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // ------------------------------------------------------------------------------------------ K1 (quad form)
 // One QUAD of lanes per (member, sub-catchment) item, 8 items per warp in day lock-step (simplyp_quad.cuh).
 // Shared memory: one QuadMem per quad, then the forcing ring.
-template <bool CAL>
+enum { MODE_RUN = 0, MODE_CAL = 1, MODE_PILOT = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ unsigned s_vblock;
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
     valid = idx < a.M;
     if (!valid) idx = a.M - 1;                     // padding quads shadow the last item and write nothing
     w = 0;
-    m = (int)idx;
+    m = a.perm ? a.perm[idx] : (int)idx;
   } else {
     if (idx >= a.n_items_padded) idx = a.n_items_padded - 1;
     int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
@@ -492,7 +508,16 @@ __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
   q.tab = s_exp2tab;
   QuadMem& qm = qmem[threadIdx.x >> 2];
   ThreadCounters cnt;
-  if (CAL) {
+  if (MODE == MODE_PILOT) {
+    PilotIO io(a, m, s, ring);
+    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    if (valid && q.ql == 0) {
+      const unsigned c = (unsigned)cnt.steps;
+      a.cost[m] = c;
+      atomicAdd(&a.hist[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+    }
+    return;
+  } else if (MODE == MODE_CAL) {
     CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
     run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
     if (valid && q.ql == 0) io.finalise();
@@ -509,6 +534,35 @@ __global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
     dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
     dg[SIMPLYP_DG_STATUS] = cnt.status;
   }
+}
+
+// ------------------------------------------------------------------------------------------ cost ordering
+// Counting sort of the members by pilot cost, heaviest first: hist[] -> start offsets (one block), then scatter.
+__global__ void cost_scan_kernel(unsigned* hist) {
+  __shared__ unsigned part[1024];
+  constexpr int PER = COST_BUCKETS / 1024;
+  // thread t owns buckets [PER*t, PER*t+PER) counted from the TOP (descending cost)
+  unsigned loc[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { loc[k] = hist[COST_BUCKETS - 1 - (PER * threadIdx.x + k)]; sum += loc[k]; }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {            // inclusive Hillis-Steele scan
+    const unsigned v = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned run = part[threadIdx.x] - sum;         // exclusive prefix of this thread's first bucket
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { hist[COST_BUCKETS - 1 - (PER * threadIdx.x + k)] = run; run += loc[k]; }
+}
+__global__ void cost_scatter_kernel(const unsigned* cost, unsigned* offsets, int* perm, int M) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const unsigned c = cost[m];
+  const unsigned pos = atomicAdd(&offsets[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+  perm[pos] = m;
 }
 
 // ------------------------------------------------------------------------------------------ obs constants
@@ -596,7 +650,8 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_ticket, off_progress, off_flux, total;
+  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_ticket,
+      off_progress, off_flux, total;
 };
 
 WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
@@ -608,6 +663,9 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
   L.off_lvl_items = o; o = align_up(o + sizeof(long long) * ((size_t)d.n_sc + 1));   // at most n_sc levels
   L.off_lvl_order = o; o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
   L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
+  L.off_cost = o;  o = align_up(o + sizeof(unsigned) * (size_t)d.n_members);
+  L.off_hist = o;  o = align_up(o + sizeof(unsigned) * COST_BUCKETS);
+  L.off_perm = o;  o = align_up(o + sizeof(int) * (size_t)d.n_members);
   L.off_ticket = o; o = align_up(o + sizeof(int));
   L.off_progress = o;
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
@@ -649,6 +707,31 @@ int pick_block(long long n_threads, int requested) {
 }
 
 // Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.
+// Pilot + counting sort: fills a.perm (one sub-catchment, quad kernel).  3 small launches + the pilot.
+int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KArgs& a, const WsLayout& L, char* ws,
+                          cudaStream_t st) {
+  const int days = opt.pilot_days > 0 ? opt.pilot_days : 8;
+  if (opt.pilot_days < 0 || !ws || dims.n_sc != 1 || dims.n_members < 512 || dims.n_days < 8 * days) return SIMPLYP_OK;
+  KArgs p = a;
+  p.D = days;
+  p.diag = nullptr;
+  p.perm = nullptr;
+  p.cost = reinterpret_cast<unsigned*>(ws + L.off_cost);
+  p.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
+  int* perm = reinterpret_cast<int*>(ws + L.off_perm);
+  SP_CUDA(cudaMemsetAsync(p.hist, 0, sizeof(unsigned) * COST_BUCKETS, st));
+  const int block = 128, qpb = block / 4;
+  const long long grid = ((long long)dims.n_members + qpb - 1) / qpb;
+  const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
+  simplyp_quad_kernel<MODE_PILOT><<<(unsigned)grid, block, smem, st>>>(p);
+  cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
+  cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members);
+  g_launches.fetch_add(3);
+  SP_CUDA(cudaGetLastError());
+  a.perm = perm;
+  return SIMPLYP_OK;
+}
+
 template <bool CAL>
 int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, const int32_t* po_host,
                   const int32_t* pid_host, char* ws, cudaStream_t st) {
@@ -721,7 +804,9 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const int qpb = block / 4;
     const long long grid = (n_items_padded + qpb - 1) / qpb;
     const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
-    simplyp_quad_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
+    const int rc = order_members_by_cost(dims, opt, a, L, ws, st);
+    if (rc) return rc;
+    simplyp_quad_kernel<CAL ? MODE_CAL : MODE_RUN><<<(unsigned)grid, block, smem, st>>>(a);
   }
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());

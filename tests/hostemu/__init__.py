@@ -74,3 +74,12 @@ def quad_rhs_check(member_row, sc_row, P, E, doy, us, y7, dynamic_epc0=1, dynami
     y7 = np.ascontiguousarray(y7, dtype=np.float64)
     return float(lib.hostemu_quad_rhs_check(mp.ctypes.data, sp.ctypes.data, P, E, doy, us.ctypes.data,
                                             y7.ctypes.data, dynamic_epc0, dynamic_erod))
+
+
+def exp_tab(x):
+    """sp_exp_tab of simplyp_core.cuh evaluated on the host."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib.hostemu_exp_tab(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_int(x.size))
+    return y

@@ -145,3 +145,7 @@ extern "C" double hostemu_quad_rhs_check(const double* mp, const double* sp, dou
   }
   return worst;
 }
+
+extern "C" void hostemu_exp_tab(const double* x, double* y, int n) {
+  for (int i = 0; i < n; ++i) y[i] = sp_exp_tab(x[i], kExp2Tab);
+}
