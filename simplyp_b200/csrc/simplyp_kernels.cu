@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -444,9 +445,12 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // ------------------------------------------------------------------------------------------ K1 (quad form)
 // One QUAD of lanes per (member, sub-catchment) item, 8 items per warp in day lock-step (simplyp_quad.cuh).
 // Shared memory: one QuadMem per quad, then the forcing ring.
+// MINB = resident blocks per SM the register allocation is made for: 4 (128 registers, 16 warps per SM) when the
+// ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
+// instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
 enum { MODE_RUN = 0, MODE_CAL = 1, MODE_PILOT = 2 };
-template <int MODE>
-__global__ void __launch_bounds__(128, 4) simplyp_quad_kernel(const KArgs a) {
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ unsigned s_vblock;
   __shared__ double s_exp2tab[32];
@@ -707,6 +711,16 @@ int pick_block(long long n_threads, int requested) {
 }
 
 // Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.
+// Register budget of the quad kernel for a grid of `grid` blocks (see the kernel's comment).
+int quad_minblocks(long long grid) {
+  if (const char* e = getenv("SIMPLYP_QUAD_MINBLOCKS")) { const int v = atoi(e); if (v >= 2 && v <= 4) return v; }
+  int dev = 0, n_sm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (grid <= 2ll * n_sm + n_sm / 4) return 2;      // all (or all but the lightest few) blocks resident at 2 per SM
+  if (grid <= 3ll * n_sm + n_sm / 4) return 3;
+  return 4;
+}
+
 // Pilot + counting sort: fills a.perm (one sub-catchment, quad kernel).  3 small launches + the pilot.
 int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KArgs& a, const WsLayout& L, char* ws,
                           cudaStream_t st) {
@@ -723,7 +737,9 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   const int block = 128, qpb = block / 4;
   const long long grid = ((long long)dims.n_members + qpb - 1) / qpb;
   const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
-  simplyp_quad_kernel<MODE_PILOT><<<(unsigned)grid, block, smem, st>>>(p);
+  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE_PILOT, 2><<<(unsigned)grid, block, smem, st>>>(p);
+  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE_PILOT, 3><<<(unsigned)grid, block, smem, st>>>(p);
+  else simplyp_quad_kernel<MODE_PILOT, 4><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
   cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members);
   g_launches.fetch_add(3);
@@ -806,7 +822,10 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
     const int rc = order_members_by_cost(dims, opt, a, L, ws, st);
     if (rc) return rc;
-    simplyp_quad_kernel<CAL ? MODE_CAL : MODE_RUN><<<(unsigned)grid, block, smem, st>>>(a);
+    constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
+    if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2><<<(unsigned)grid, block, smem, st>>>(a);
+    else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3><<<(unsigned)grid, block, smem, st>>>(a);
+    else simplyp_quad_kernel<MODE, 4><<<(unsigned)grid, block, smem, st>>>(a);
   }
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());
