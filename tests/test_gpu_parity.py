@@ -4,6 +4,7 @@ tolerances (rtol=1e-7, atol=1e-10) versus the reference's odeint path run at tig
 (rtol=1e-10, atol=1e-13); see tests/parity.py."""
 import json
 import os
+import sys
 
 import numpy as np
 import pandas as pd
@@ -13,6 +14,7 @@ from tests import parity
 from tests.util import max_rel
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -242,3 +244,68 @@ def test_edge_cases(cabi):
     # bad arguments come back as errors, not crashes
     with pytest.raises(cabi.SimplypError):
         cabi.run_host(forcing, member, sc, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32), opt)
+
+
+def _device_run(w, n_days=None, keep=None):
+    """Full-output run through the device-pointer C-ABI (torch holds the buffers); returns (out, diag) on the GPU."""
+    import torch
+    from simplyp_b200 import packing as pk
+    from simplyp_b200.engine import Engine
+    eng = Engine(0)
+    forcing = w["forcing"] if n_days is None else w["forcing"][:n_days]
+    topo, sc = w["topo"], w["sc"]
+    if keep is not None:                      # prune to a set of reaches that is closed under "upstream of"
+        from simplyp_b200 import packing as pk2
+        p_struc = w["p_struc"].loc[[topo.sc_ids[i] for i in keep]]
+        topo = pk2.build_topology(p_struc, [topo.sc_ids[i] for i in keep])
+        sc = sc[:, keep]
+    opt = w["opt"]
+    out, diag = eng.run(eng.to_device(forcing), eng.to_device(w["member"]), eng.to_device(sc), topo.parent_offsets,
+                        topo.parent_ids, opt)
+    torch.cuda.synchronize()
+    return out, diag
+
+
+def _upstream_closure(topo, i):
+    keep, stack = set(), [i]
+    while stack:
+        j = stack.pop()
+        if j in keep:
+            continue
+        keep.add(j)
+        stack.extend(int(p) for p in topo.parent_ids[topo.parent_offsets[j]:topo.parent_offsets[j + 1]])
+    return sorted(keep)
+
+
+@pytest.mark.parametrize("cfg", [3, 5])
+def test_scale_configs_full_size_properties(cabi, cfg):
+    """BASELINE configs 3 (256 reaches, 30 years) and 5 (4096 reaches x 3 land uses, 50 years, 15 GB of daily
+    output kept in HBM) at FULL size, through properties that need no oracle:
+    (a) every value finite, no integrator status bit;
+    (b) causality in time: the first 300 days of the long run equal a 300-day run, bitwise;
+    (c) locality in the reach DAG: a reach's series depends only on its upstream sub-network — the network pruned
+        to the upstream closure of one reach gives the same bits for those reaches;
+    (d) the reach volume stays on ode_f's invariant curve Vr = L/(a_Q 86400) Qr^(1-b_Q) (:127-131, :457-459)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import exp_configs
+    from simplyp_b200 import packing as pk
+    w = exp_configs.build(cfg)
+    # the reference's leaked NC_type (model.py:442,676) couples every reach to the LAST one of the run order, so
+    # locality only holds with that quirk off
+    w["opt"].strict_quirks = 0
+    topo = w["topo"]
+    out, diag = _device_run(w)
+    assert bool(torch.isfinite(out).all().item()) and int(diag[..., 3].max().item()) == 0
+    out_p, _ = _device_run(w, n_days=300)
+    assert bool(torch.equal(out[:, :, :300], out_p))
+    target = topo.n_sc // 3
+    keep = sorted(set(_upstream_closure(topo, target)) | {0})     # reach 0 is p['SC_Qr0'] (initial flow, :386)
+    assert 1 <= len(keep) < topo.n_sc
+    out_k, _ = _device_run(w, n_days=300, keep=keep)
+    assert bool(torch.equal(out_k, out[:, keep][:, :, :300]))
+    Qr, Vr = out[0, :, :, 4], out[0, :, :, 3]
+    aQ, bQ = w["member"][0, pk.MEMBER_INDEX["a_Q"]], w["member"][0, pk.MEMBER_INDEX["b_Q"]]
+    L = torch.from_numpy(w["sc"][0, :, pk.SC_INDEX["L_reach"]]).to(out.device)[:, None]
+    rel = ((Vr - L / (aQ * 86400.0) * Qr ** (1 - bQ)).abs() / Vr).max().item()
+    assert rel < 1e-5, rel
