@@ -212,7 +212,7 @@ def run_ours(args):
     opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol,
                            lanes_per_item=args.lanes)
     opt.pilot_days = args.pilot_days
-    kernel_name = "simplyp_integrate_kernel<true>" if args.lanes == 1 else "simplyp_quad_kernel<true>"
+    kernel_name = "simplyp_integrate_kernel<cal>" if args.lanes == 1 else "simplyp_quad_kernel<cal>"
     eng = Engine(local_rank)
     S, D, V = w["topo"].n_sc, w["forcing"].shape[0], w["obs_m"].shape[0]
 
@@ -300,6 +300,14 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = None, None
+        try:     # measured DRAM traffic of this kernel at this size, from the committed ncu capture (null if none)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get("%s|%d|%d" % (kernel_name, hi - lo, D))
+            if ent:
+                traffic, traffic_src = ent["bytes"], ent["source"]
+        except Exception:
+            pass
         alg_bytes = (d_forc.numel() + d_mem.numel() + d_sc.numel() + d_obs.numel()) * 8 + stats.numel() * 8 * 2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -315,7 +323,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "simplyp_calibrate_host (C-ABI, pinned host buffers)", "matches_device_leg": same},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / fp64_peak) if fp64_peak else None, "traffic": None,
+                         "frac": (achieved_tf / fp64_peak) if fp64_peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": "simplyp_measure_fp64_peak (DFMA probe, this run); MEASURED_PEAKS.json has no FP64 figure",
                          "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_launch": flops_local,
