@@ -291,7 +291,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = M_total * S * D * args.steps / float(e2e_s.item())
-    same = bool(np.array_equal(st_host, stats.cpu().numpy()))
+    same = bool(np.array_equal(st_host, stats.cpu().numpy(), equal_nan=True))
 
     if rank == 0:
         peaks = {}

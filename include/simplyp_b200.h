@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SIMPLYP_ABI_VERSION 1
+#define SIMPLYP_ABI_VERSION 2
 
 /* error codes */
 #define SIMPLYP_OK          0
@@ -137,7 +137,10 @@ enum {
   SIMPLYP_ST_PBIAS,      /* 100 sum(s-o)/sum(o)                       :448                 */
   SIMPLYP_ST_NRMSD,      /* 100 mean|s-o| / std(o) (population std)   :449                 */
   SIMPLYP_ST_SSE,        /* sum((o-s)^2)                                                   */
-  SIMPLYP_NSTAT
+  SIMPLYP_ST_SPEARMAN,   /* Spearman's rank correlation (average ranks for ties)  :444-445 ; NaN unless
+                            SimplypOptions.rank_stats is set                                    */
+  SIMPLYP_ST_RESERVED,
+  SIMPLYP_NSTAT          /* = 10 */
 };
 
 /* Integrator diagnostics per (member, sub-catchment): diag[M][S][SIMPLYP_NDIAG] (int64) */
@@ -173,7 +176,9 @@ typedef struct SimplypOptions {
                                 kernel), 4, or 1 (one thread per item, the round-1 kernel kept for A/B runs) */
   int32_t pilot_days;        /* ensembles of one sub-catchment: days of the pilot run whose step counts order the
                                 members over the lock-step warps (0 = default 8, < 0 = no pilot) */
-  int32_t reserved[3];
+  int32_t rank_stats;        /* calibration: also reduce Spearman's r (stores the simulated value of every observed
+                                day, M*V*D*8 bytes of workspace, and ranks them on the device afterwards) */
+  int32_t reserved[2];
 } SimplypOptions;
 
 /* ---- entry points -------------------------------------------------------------------------- */
@@ -191,7 +196,9 @@ void        simplyp_default_options(SimplypOptions* opt);
 int simplyp_topology_levels(int32_t n_sc, const int32_t* parent_offsets, const int32_t* parent_ids,
                             int32_t* levels);
 
-/* Bytes of device workspace simplyp_*_device needs for these dims (flux exchange + flags). */
+/* Bytes of device workspace simplyp_*_device needs for these dims (flux exchange, flags, cost ordering).
+ * `calibrate`: 0 = simplyp_run_device, 1 = simplyp_calibrate_device, 3 = simplyp_calibrate_device with
+ * SimplypOptions.rank_stats set.  dims->reserved[0] must hold the number of edges of the reach topology. */
 int64_t simplyp_workspace_bytes(const SimplypDims* dims, int calibrate);
 
 /* Full-output integration (replaces model.py:365-724 for every member):
@@ -212,6 +219,15 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
                              const int32_t* parent_offsets, const int32_t* parent_ids,
                              const double* obs, const int32_t* obs_desc,
                              double* stats, int64_t* diag, void* workspace, void* stream);
+
+/* sum_to_waterbody (model.py:851-900) on the raw output of simplyp_run_device, for every member and day:
+ *   out[M][S][D][25], reaches[n_reaches] = run-order indices of the reaches with In_final_flux? == 1 (device),
+ *   waterbody[M][D][SIMPLYP_NWB] = Q_cumecs, Msus_kg/day, TDP_kg/day, PP_kg/day, SS_mgl, TDP_mgl, PP_mgl,
+ *                                  TP_mgl, TP_kg/day, SRP_mgl, SRP_kg/day  (:878-892, derived_P_species :840-845) */
+#define SIMPLYP_NWB 11
+int simplyp_sum_to_waterbody_device(const SimplypDims* dims, const double* out, const double* sc_params,
+                                    const double* member_params, const int32_t* reaches, int32_t n_reaches,
+                                    double* waterbody, void* stream);
 
 /* Host-buffer forms: same arguments as HOST pointers; the library stages them through its own
  * (cached) device buffers on `device`, runs and copies the result back before returning. */

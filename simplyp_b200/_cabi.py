@@ -22,7 +22,7 @@ EXPORTS = [
     "simplyp_default_options", "simplyp_topology_levels", "simplyp_workspace_bytes",
     "simplyp_run_device", "simplyp_calibrate_device", "simplyp_run_host", "simplyp_calibrate_host",
     "simplyp_release_cache", "simplyp_launch_count", "simplyp_measure_fp64_peak",
-    "simplyp_measure_fp64_latency",
+    "simplyp_measure_fp64_latency", "simplyp_sum_to_waterbody_device",
 ]
 
 
@@ -36,7 +36,7 @@ class SimplypOptions(C.Structure):
                 ("max_steps_per_day", C.c_int32), ("dynamic_epc0", C.c_int32),
                 ("dynamic_erodibility", C.c_int32), ("run_mode_cal", C.c_int32), ("sc_qr0", C.c_int32),
                 ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("lanes_per_item", C.c_int32),
-                ("pilot_days", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("pilot_days", C.c_int32), ("rank_stats", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class SimplypError(RuntimeError):
@@ -84,7 +84,9 @@ def load():
     lib.simplyp_measure_fp64_peak.restype = C.c_double
     lib.simplyp_measure_fp64_latency.argtypes = [C.c_int]
     lib.simplyp_measure_fp64_latency.restype = C.c_double
-    if lib.simplyp_abi_version() != 1:
+    lib.simplyp_sum_to_waterbody_device.argtypes = [C.POINTER(SimplypDims), vp, vp, vp, vp, C.c_int32, vp, vp]
+    lib.simplyp_sum_to_waterbody_device.restype = C.c_int
+    if lib.simplyp_abi_version() != 2:
         raise SimplypError("ABI version mismatch")
     _lib = lib
     return lib
@@ -218,8 +220,14 @@ def calibrate_device(dims, opt, forcing_ptr, member_ptr, sc_ptr, parent_offsets,
                                         _iptr(pid), obs_ptr, desc_ptr, stats_ptr, diag_ptr, ws_ptr, stream_ptr))
 
 
-def workspace_bytes(dims, calibrate):
-    n = load().simplyp_workspace_bytes(C.byref(dims), 1 if calibrate else 0)
+def sum_to_waterbody_device(dims, out_ptr, sc_ptr, member_ptr, reaches_ptr, n_reaches, wb_ptr, stream_ptr):
+    lib = require_device()
+    _check(lib.simplyp_sum_to_waterbody_device(C.byref(dims), out_ptr, sc_ptr, member_ptr, reaches_ptr,
+                                               int(n_reaches), wb_ptr, stream_ptr))
+
+
+def workspace_bytes(dims, calibrate, rank_stats=False):
+    n = load().simplyp_workspace_bytes(C.byref(dims), (1 if calibrate else 0) | (2 if (calibrate and rank_stats) else 0))
     if n < 0:
         _check(int(n))
     return int(n)

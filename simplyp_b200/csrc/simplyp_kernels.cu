@@ -73,6 +73,7 @@ struct KArgs {
   long long n_items_padded;
   // cost ordering of an ensemble (quad kernel, one sub-catchment): a short pilot run counts the step attempts
   // of every member; members are then dealt to the lock-step warps heaviest first
+  double* sim_obs;              // cal + rank statistics: [M][V][D] simulated value on observed days, or null
   const int* perm;              // [M] member handled by item idx, or null
   unsigned* cost;               // pilot: [M] step attempts
   unsigned* hist;               // pilot: [COST_BUCKETS] histogram of the costs
@@ -82,7 +83,7 @@ constexpr int COST_BUCKETS = 4096;
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
 enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
 // obs_const[V][8]
-enum { OC_N = 0, OC_MEAN, OC_SS, OC_MEAN_LOG, OC_SS_LOG, OC_SUM, OC_STD };
+enum { OC_N = 0, OC_MEAN, OC_SS, OC_MEAN_LOG, OC_SS_LOG, OC_SUM, OC_STD, OC_SS_RANK };
 
 // ------------------------------------------------------------------------------------------ K1a forcing ring
 // The daily forcing (32 B/day, shared by every member and sub-catchment) is staged per block in a ring of
@@ -330,6 +331,7 @@ struct CalIO : IOBase {
         case SIMPLYP_V_TP:  sim = tdp + pp; break;
         default:            sim = tdp * f_TDP; break;
       }
+      if (a.sim_obs != nullptr) a.sim_obs[((size_t)m * a.V + v) * a.D + day] = sim;
       const double* oc = a.obs_const + 8 * v;
       const double mo = __ldg(oc + OC_MEAN);
       const double em = __ldg(a.member_params + (size_t)m * SIMPLYP_NP_MEMBER + SIMPLYP_P_ERR_M0 + kind);
@@ -366,6 +368,8 @@ struct CalIO : IOBase {
       rs[SIMPLYP_ST_PBIAS] = 100.0 * (s1 + n * oc[OC_MEAN] - sum_o) / sum_o;
       rs[SIMPLYP_ST_NRMSD] = 100.0 * (sabs / n) / std_o;
       rs[SIMPLYP_ST_SSE] = sse;
+      rs[SIMPLYP_ST_SPEARMAN] = NAN;            // filled by spearman_kernel when rank statistics are on
+      rs[SIMPLYP_ST_RESERVED] = 0.0;
     }
   }
 };
@@ -540,6 +544,142 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------ rank statistics
+// Spearman's r (visualise_results.py:444-445: pandas corr(method='spearman') = Pearson correlation of average
+// ranks).  The observation ranks are shared by all members: one block per series ranks them once
+// (obs_rank[v][d], NaN where there is no observation) and stores the sum of squares about the mean rank.
+__global__ void obs_rank_kernel(const double* obs, int D, double* obs_rank, double* obs_const) {
+  const int v = blockIdx.x;
+  const double* o = obs + (size_t)v * D;
+  double* rk = obs_rank + (size_t)v * D;
+  __shared__ double red[256];
+  const double n = obs_const[8 * v + OC_N];
+  const double mean_rank = 0.5 * (n + 1.0);
+  double ss = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double x = o[d];
+    double r = NAN;
+    if (x == x) {
+      int less = 0, equal = 0;
+      for (int j = 0; j < D; ++j) { const double y = o[j]; less += (y < x); equal += (y == x); }
+      r = less + 0.5 * (equal + 1);                 // average rank of a tie group
+      ss += (r - mean_rank) * (r - mean_rank);
+    }
+    rk[d] = r;
+  }
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) obs_const[8 * v + OC_SS_RANK] = red[0];
+}
+
+// One block per (member, series): the simulated values of the observed days are compacted into shared memory
+// together with the observation ranks, ranked by counting (ties share the mean rank) and correlated.
+// Dynamic shared memory: 2 * cap doubles; a series longer than `cap` gets NaN.
+__global__ void spearman_kernel(const double* sim_obs, const double* obs_rank, const double* obs_const, int V, int D,
+                                int cap, double* stats) {
+  extern __shared__ double sh[];
+  double* s_sim = sh;
+  double* s_rk = sh + cap;
+  __shared__ int s_n;
+  __shared__ double red[2][128];
+  const int mv = blockIdx.x, v = mv % V;
+  const double* sim = sim_obs + (size_t)mv * D;
+  const double* rk = obs_rank + (size_t)v * D;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double r = rk[d];
+    if (r == r) {
+      const double x = sim[d];
+      if (x == x) {                                 // pairs with a NaN on either side are dropped (:435-436)
+        const int k = atomicAdd(&s_n, 1);
+        if (k < cap) { s_sim[k] = x; s_rk[k] = r; }
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  double* out = stats + (size_t)mv * SIMPLYP_NSTAT + SIMPLYP_ST_SPEARMAN;
+  if (n > cap || n < 2) { if (threadIdx.x == 0) *out = NAN; return; }
+  // a NaN simulated value changes the set of pairs: the observation ranks must then be recomputed among the
+  // pairs kept (pandas ranks after dropna) — rare (a failed member); detected by comparing n with the series' n
+  const bool rerank_obs = (double)n != obs_const[8 * v + OC_N];
+  const double mean_rank = 0.5 * (n + 1.0);
+  double sxy = 0.0, sxx = 0.0, syy = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = s_sim[i];
+    int less = 0, equal = 0;
+    for (int j = 0; j < n; ++j) { const double y = s_sim[j]; less += (y < x); equal += (y == x); }
+    const double rs = less + 0.5 * (equal + 1);
+    double ro = s_rk[i];
+    if (rerank_obs) {
+      int l2 = 0, e2 = 0;
+      for (int j = 0; j < n; ++j) { const double y = s_rk[j]; l2 += (y < ro); e2 += (y == ro); }
+      ro = l2 + 0.5 * (e2 + 1);
+      syy += (ro - mean_rank) * (ro - mean_rank);
+    }
+    sxy += (rs - mean_rank) * (ro - mean_rank);
+    sxx += (rs - mean_rank) * (rs - mean_rank);
+  }
+  red[0][threadIdx.x] = sxy; red[1][threadIdx.x] = sxx;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) { red[0][threadIdx.x] += red[0][threadIdx.x + k]; red[1][threadIdx.x] += red[1][threadIdx.x + k]; }
+    __syncthreads();
+  }
+  const double cxy = red[0][0], cxx = red[1][0];
+  __syncthreads();
+  if (rerank_obs) {
+    red[0][threadIdx.x] = syy;
+    __syncthreads();
+    for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+      if (threadIdx.x < k) red[0][threadIdx.x] += red[0][threadIdx.x + k];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double cyy = rerank_obs ? red[0][0] : obs_const[8 * v + OC_SS_RANK];
+    *out = cxy / sqrt(cxx * cyy);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ waterbody sums
+// sum_to_waterbody (model.py:851-900) on the raw output: for every (member, day) the reaches flagged
+// In_final_flux? == 1 are summed — Q_cumecs (= Qr*A_catch*1000/86400, :784), Msus/TDP/PP daily fluxes — and the
+// concentrations (:889-892) and derived species (derived_P_species, :831-847) follow.  One thread per (member, day);
+// consecutive threads take consecutive days, so the strided row reads of a warp fall in neighbouring rows.
+// wb[m][d][SIMPLYP_NWB] = Q_cumecs, Msus_kg/day, TDP_kg/day, PP_kg/day, SS_mgl, TDP_mgl, PP_mgl, TP_mgl,
+//                          TP_kg/day, SRP_mgl, SRP_kg/day
+__global__ void waterbody_kernel(const double* out, const double* sc_params, const double* member_params,
+                                 const int* reaches, int n_reaches, int M, int S, int D, int Msc, double* wb) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * D) return;
+  const int m = (int)(idx / D), d = (int)(idx - (long long)m * D);
+  const double* scp = sc_params + (size_t)(Msc > 1 ? m : 0) * S * SIMPLYP_NP_SC;
+  double q = 0.0, ms = 0.0, td = 0.0, pp = 0.0;
+  for (int k = 0; k < n_reaches; ++k) {
+    const int s = reaches[k];
+    const double* row = out + (((size_t)m * S + s) * D + d) * SIMPLYP_NOUT;
+    q += row[SIMPLYP_O_QR] * scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH] * 1000.0 / 86400.0;
+    ms += row[SIMPLYP_O_MSUS_FLUX];
+    td += row[SIMPLYP_O_TDP_FLUX];
+    pp += row[SIMPLYP_O_PP_FLUX];
+  }
+  const double f_TDP = member_params[(size_t)m * SIMPLYP_NP_MEMBER + SIMPLYP_P_F_TDP];
+  const double c = 1000.0 / 86400.0;
+  double* w = wb + (size_t)idx * SIMPLYP_NWB;
+  const double ss_mgl = (ms / q) * c, tdp_mgl = (td / q) * c, pp_mgl = (pp / q) * c;
+  w[0] = q; w[1] = ms; w[2] = td; w[3] = pp; w[4] = ss_mgl; w[5] = tdp_mgl; w[6] = pp_mgl;
+  w[7] = tdp_mgl + pp_mgl;        // TP_mgl   (:842)
+  w[8] = td + pp;                 // TP_kg/day (:843)
+  w[9] = tdp_mgl * f_TDP;         // SRP_mgl  (:844)
+  w[10] = td * f_TDP;             // SRP_kg/day (:845)
+}
+
 // ------------------------------------------------------------------------------------------ cost ordering
 // Counting sort of the members by pilot cost, heaviest first: hist[] -> start offsets (one block), then scatter.
 __global__ void cost_scan_kernel(unsigned* hist) {
@@ -655,10 +795,10 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
   size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_ticket,
-      off_progress, off_flux, total;
+      off_progress, off_flux, off_obs_rank, off_sim_obs, total;
 };
 
-WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
+WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = false) {
   WsLayout L;
   size_t o = 0;
   L.off_po = o;    o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
@@ -675,6 +815,10 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal) {
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
   L.off_flux = o;
   if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
+  L.off_obs_rank = o;
+  if (cal && ranks) o = align_up(o + sizeof(double) * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1) * d.n_days);
+  L.off_sim_obs = o;
+  if (cal && ranks) o = align_up(o + sizeof(double) * (size_t)d.n_members * (d.n_obs_series > 0 ? d.n_obs_series : 1) * d.n_days);
   L.total = o;
   return L;
 }
@@ -917,7 +1061,7 @@ int simplyp_topology_levels(int32_t n_sc, const int32_t* parent_offsets, const i
 
 int64_t simplyp_workspace_bytes(const SimplypDims* dims, int calibrate) {
   if (!dims) return SIMPLYP_EINVAL;
-  return (int64_t)ws_layout(*dims, dims->reserved[0], calibrate != 0).total;
+  return (int64_t)ws_layout(*dims, dims->reserved[0], (calibrate & 1) != 0, (calibrate & 2) != 0).total;
 }
 
 int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
@@ -948,7 +1092,8 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
   if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int V = dims->n_obs_series;
-  const WsLayout L = ws_layout(*dims, parent_offsets[dims->n_sc], true);
+  const bool ranks = opt->rank_stats != 0 && V > 0 && dims->n_days > 0;
+  const WsLayout L = ws_layout(*dims, parent_offsets[dims->n_sc], true, ranks);
   char* ws = static_cast<char*>(workspace);
   KArgs a = base_args(*dims, *opt, forcing, member_params, sc_params);
   a.diag = reinterpret_cast<long long*>(diag);
@@ -956,16 +1101,39 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
   a.obs_desc = obs_desc;
   a.stats = stats;
   a.obs_const = reinterpret_cast<const double*>(ws + L.off_oc);
+  double* obs_rank = reinterpret_cast<double*>(ws + L.off_obs_rank);
   if (V > 0) {
     SP_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * SIMPLYP_NSTAT * (size_t)dims->n_members * V, st));
     if (dims->n_days > 0) {
       obs_const_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, reinterpret_cast<double*>(ws + L.off_oc));
       g_launches.fetch_add(1);
+      if (ranks) {
+        obs_rank_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, obs_rank, reinterpret_cast<double*>(ws + L.off_oc));
+        g_launches.fetch_add(1);
+        a.sim_obs = reinterpret_cast<double*>(ws + L.off_sim_obs);
+        // a day without a finite simulated value must read as NaN (dropped pair)
+        SP_CUDA(cudaMemsetAsync(a.sim_obs, 0xff, sizeof(double) * (size_t)dims->n_members * V * dims->n_days, st));
+      }
       SP_CUDA(cudaGetLastError());
     }
   }
   if (dims->n_days == 0) return SIMPLYP_OK;
-  return launch_levels<true>(*dims, *opt, a, parent_offsets, parent_ids, ws, st);
+  rc = launch_levels<true>(*dims, *opt, a, parent_offsets, parent_ids, ws, st);
+  if (rc) return rc;
+  if (ranks) {
+    // shared memory: sim values + obs ranks of one series; at most one entry per day
+    int cap = dims->n_days;
+    const int cap_max = (200 * 1024) / 16;
+    if (cap > cap_max) cap = cap_max;
+    const size_t smem = (size_t)cap * 2 * sizeof(double);
+    if (smem > 48 * 1024)
+      SP_CUDA(cudaFuncSetAttribute(spearman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spearman_kernel<<<(unsigned)((size_t)dims->n_members * V), 128, smem, st>>>(
+        a.sim_obs, obs_rank, a.obs_const, V, dims->n_days, cap, stats);
+    g_launches.fetch_add(1);
+    SP_CUDA(cudaGetLastError());
+  }
+  return SIMPLYP_OK;
 }
 
 int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
@@ -1019,7 +1187,7 @@ int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOpt
   const size_t b_stats = sizeof(double) * SIMPLYP_NSTAT * M * V, b_diag = sizeof(int64_t) * SIMPLYP_NDIAG * M * S;
   SimplypDims d2 = *dims;
   d2.reserved[0] = parent_offsets[S];
-  const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, 1);
+  const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, opt->rank_stats ? 3 : 1);
   void *d_forc, *d_mp, *d_sc, *d_obs, *d_desc, *d_stats, *d_diag, *d_ws;
   if ((rc = cache_get(0, b_forc, &d_forc)) || (rc = cache_get(1, b_mp, &d_mp)) || (rc = cache_get(2, b_sc, &d_sc)) ||
       (rc = cache_get(3, b_stats, &d_stats)) || (rc = cache_get(4, b_diag, &d_diag)) ||
@@ -1037,6 +1205,23 @@ int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOpt
   SP_CUDA(cudaMemcpyAsync(stats, d_stats, b_stats, cudaMemcpyDeviceToHost, st));
   if (diag) SP_CUDA(cudaMemcpyAsync(diag, d_diag, b_diag, cudaMemcpyDeviceToHost, st));
   SP_CUDA(cudaStreamSynchronize(st));
+  return SIMPLYP_OK;
+}
+
+int simplyp_sum_to_waterbody_device(const SimplypDims* dims, const double* out, const double* sc_params,
+                                    const double* member_params, const int32_t* reaches, int32_t n_reaches,
+                                    double* waterbody, void* stream) {
+  if (!dims || !out || !sc_params || !member_params || !reaches || !waterbody)
+    return fail(SIMPLYP_EINVAL, "null argument%s");
+  if (n_reaches <= 0 || n_reaches > dims->n_sc) return fail(SIMPLYP_EINVAL, "bad number of waterbody reaches%s");
+  if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  const long long n = (long long)dims->n_members * dims->n_days;
+  if (n == 0) return SIMPLYP_OK;
+  waterbody_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, sc_params, member_params, reaches, n_reaches, dims->n_members, dims->n_sc, dims->n_days,
+      dims->n_sc_param_sets, waterbody);
+  g_launches.fetch_add(1);
+  SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;
 }
 

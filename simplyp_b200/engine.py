@@ -98,17 +98,38 @@ class Engine:
         chunk = M
         if S > 1:
             budget = max_workspace_bytes if max_workspace_bytes is not None else self.free_bytes() // 2
-            per_member = 32 * S * D
+            per_member = 32 * S * D + (8 * V * D if opt.rank_stats else 0)
             chunk = max(1, min(M, int(budget // max(per_member, 1))))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             for m0 in range(0, M, chunk):
                 m1 = min(M, m0 + chunk)
                 dims = _cabi.make_dims(m1 - m0, S, D, 1 if Msc == 1 else (m1 - m0), V, n_edges)
-                ws = self._workspace(_cabi.workspace_bytes(dims, True))
+                ws = self._workspace(_cabi.workspace_bytes(dims, True, bool(opt.rank_stats)))
                 scp = sc_params if Msc == 1 else sc_params[m0:m1]
                 _cabi.calibrate_device(dims, opt, forcing.data_ptr(), member_params[m0:m1].data_ptr(),
                                        scp.data_ptr(), parent_offsets, parent_ids, obs.data_ptr(),
                                        obs_desc.data_ptr(), stats[m0:m1].data_ptr(), diag[m0:m1].data_ptr(),
                                        ws.data_ptr(), stream)
         return stats, diag
+
+    # ------------------------------------------------------------------ receiving water body
+    WATERBODY_COLUMNS = ["Q_cumecs", "Msus_kg/day", "TDP_kg/day", "PP_kg/day", "SS_mgl", "TDP_mgl", "PP_mgl",
+                         "TP_mgl", "TP_kg/day", "SRP_mgl", "SRP_kg/day"]
+
+    def sum_to_waterbody(self, out, member_params, sc_params, reaches):
+        """Reference ``sum_to_waterbody`` (``model.py:851-900``) for every member of a full-output run, on the
+        device: ``out`` [M][S][D][25] from :meth:`run`, ``reaches`` = run-order indices of the reaches flagged
+        ``In_final_flux? == 1``.  Returns [M][D][11] (columns ``WATERBODY_COLUMNS``); asynchronous."""
+        torch = _torch()
+        M, S, D = out.shape[0], out.shape[1], out.shape[2]
+        if sc_params.dim() == 2:
+            sc_params = sc_params.unsqueeze(0)
+        dims = _cabi.make_dims(M, S, D, sc_params.shape[0], 0, 0)
+        r = torch.as_tensor(np.asarray(reaches, dtype=np.int32), device=self.device)
+        wb = torch.empty((M, D, len(self.WATERBODY_COLUMNS)), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.sum_to_waterbody_device(dims, out.data_ptr(), sc_params.data_ptr(), member_params.data_ptr(),
+                                          r.data_ptr(), int(r.numel()), wb.data_ptr(), stream)
+        return wb

@@ -31,7 +31,7 @@ SC_INDEX = {name: i for i, name in enumerate(SC_FIELDS)}
 
 NF = 4        # forcing columns
 NOUT = 25     # raw output columns
-NSTAT = 8
+NSTAT = 10
 NDIAG = 4
 
 ODE_COLS = ["VsA", "VsS", "Vg", "Vr", "Qr_EndOfDay", "Qr", "Msus_EndOfDay", "Msus_kg/day",
@@ -43,7 +43,7 @@ RAW_COLS = ODE_COLS + NONODE_COLS
 
 VAR_KINDS = ["Q", "SS", "TDP", "PP", "TP", "SRP"]      # visualise_results.py:401
 VAR_INDEX = {v: i for i, v in enumerate(VAR_KINDS)}
-STAT_NAMES = ["n", "NSE", "log_NSE", "loglik", "r2", "pbias", "nRMSD", "SSE"]
+STAT_NAMES = ["n", "NSE", "log_NSE", "loglik", "r2", "pbias", "nRMSD", "SSE", "spearman", "reserved"]
 
 DEFAULT_ERR_M = 0.5   # likelihood error scale when the ensemble does not sample it
 

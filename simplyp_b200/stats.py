@@ -79,6 +79,26 @@ def goodness_of_fit_stats(p_SU, df_R_dict, obs_dict):
     return None
 
 
+def gof_table_from_device(member_stats, labels, n_obs=None):
+    """One member's device statistics [V][NSTAT] -> the reference's goodness-of-fit table (same columns and
+    index as ``goodness_of_fit_stats``, ``visualise_results.py:451-470``).  Needs ``rank_stats`` for Spearman's r.
+    ``n_obs[(reach, var)]`` overrides 'N obs' (the reference reports the count BEFORE aligning with the run, :429)."""
+    st = np.asarray(member_stats, dtype=float)
+    frames = []
+    for reach in dict.fromkeys(r for r, _v in labels):
+        rows, names = [], []
+        for k, (r, var) in enumerate(labels):
+            if r != reach:
+                continue
+            n = st[k, 0] if n_obs is None else n_obs[(r, var)]
+            rows.append([int(n), st[k, 1], st[k, 2], st[k, 8], st[k, 4], st[k, 5], st[k, 6]])
+            names.append(var)
+        df = pd.DataFrame(rows, columns=STATS_COLUMNS, index=names)
+        df["Reach"] = reach
+        frames.append(df)
+    return pd.concat(frames) if frames else None
+
+
 def stats_frame(member_stats, labels):
     """One member's device statistics [V][8] -> DataFrame indexed by (reach, variable)."""
     idx = pd.MultiIndex.from_tuples(labels, names=["Reach", "Variable"])

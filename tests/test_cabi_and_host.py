@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_cabi.EXPORTS) == declared
     lib2 = _cabi.load()
-    assert lib2.simplyp_abi_version() == 1
+    assert lib2.simplyp_abi_version() == 2
     assert b"sm_100a" in lib2.simplyp_version()
 
 
@@ -326,7 +326,7 @@ import torch, torch.distributed as dist
 from simplyp_b200 import ensemble as ens
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
 M, V = 11, 2
-full = torch.arange(M * V * 8, dtype=torch.float64).reshape(M, V, 8)
+full = torch.arange(M * V * 10, dtype=torch.float64).reshape(M, V, 10)
 lo, hi = ens.shard_bounds(M, 2, dist.get_rank())
 got = ens.all_gather_stats(full[lo:hi].clone(), M)
 assert got.shape == full.shape and torch.equal(got, full), (got.shape, lo, hi)

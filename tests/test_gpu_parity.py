@@ -117,7 +117,7 @@ def test_device_pointer_api_matches_host_api(cabi, golden_dir):
     torch.cuda.synchronize()
     assert np.array_equal(out_h, out_d.cpu().numpy())          # bitwise: same kernel, same inputs
     assert np.array_equal(diag_h, diag_d.cpu().numpy())
-    assert np.array_equal(st_h, st_d.cpu().numpy())
+    assert np.array_equal(st_h, st_d.cpu().numpy(), equal_nan=True)   # Spearman column is NaN without rank_stats
     # calibration statistics are consistent with the full-output series of the same run
     q = out_h[:, 0, :, 5] * 51.7 * 1000 / 86400
     o = obs_m[0]
@@ -144,7 +144,7 @@ def test_full_size_ensemble_properties(cabi):
     assert np.all(np.isfinite(st[..., :3])) and not np.any(dg[..., 3])
     lo, hi = 3331, 5017
     st2, dg2 = cabi.calibrate_host(forcing, member[lo:hi], sc[lo:hi], *args, opt)
-    assert np.array_equal(st2, st[lo:hi]) and np.array_equal(dg2, dg[lo:hi])
+    assert np.array_equal(st2, st[lo:hi], equal_nan=True) and np.array_equal(dg2, dg[lo:hi])
     opt_t = spm.make_options(p_SU, p, dyn, topo, rtol=opt.rtol / 10, atol=opt.atol / 10)
     st3, _ = cabi.calibrate_host(forcing, member[:2048], sc[:2048], *args, opt_t)
     sse, sse3 = st[:2048, :, 7], st3[:, :, 7]
@@ -309,3 +309,75 @@ def test_scale_configs_full_size_properties(cabi, cfg):
     L = torch.from_numpy(w["sc"][0, :, pk.SC_INDEX["L_reach"]]).to(out.device)[:, None]
     rel = ((Vr - L / (aQ * 86400.0) * Qr ** (1 - bQ)).abs() / Vr).max().item()
     assert rel < 1e-5, rel
+
+
+def test_device_goodness_of_fit_table_with_spearman(cabi, golden_dir):
+    """the reference's whole goodness-of-fit table (visualise_results.py:441-449, incl.
+    Spearman's r on average ranks) reduced on the device for every member of an ensemble, against
+    (a) the reference's own table for the shipped run (fixture ref_gof.json, member = shipped parameters) and
+    (b) the host table (simplyp_b200.stats.gof_one, itself pinned to the reference) built from the same members'
+        full-output series."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, stats as sps, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    opt.rank_stats = 1
+    samples = ens.latin_hypercube(40, seed=5)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    member[0] = pk.member_vector(p, p_LU)            # member 0 = the shipped parameter set
+    sc[0] = pk.sc_matrix(p_SC, topo.sc_ids)
+    forcing = pk.forcing_matrix(met)
+    variables = ("Q", "SS", "TDP", "PP", "TP", "SRP")
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, variables)
+    st, dg = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+    assert st.shape == (40, len(labels), pk.NSTAT) and not np.any(dg[..., 3])
+    out, _ = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    for i in (0, 7, 23, 39):
+        _tc, r = spm.raw_to_frames(out[i, 0], met.index, float(sc[i, 0, pk.SC_INDEX["A_catch"]]), p["Msoil_m2"],
+                                   float(member[i, pk.MEMBER_INDEX["f_TDP"]]), "None", None)
+        table = sps.gof_table_from_device(st[i], labels)
+        for k, (reach, var) in enumerate(labels):
+            want = sps.gof_one(obs[reach][var], r[sps.SIM_COLUMN[var]])
+            got = table.loc[var, sps.STATS_COLUMNS].to_numpy(dtype=float)
+            assert np.allclose(got, np.asarray(want, dtype=float), rtol=2e-6, atol=2e-6), (i, var, got, want)
+    # (a) the reference's own table (dynamic options on, shipped parameters), at the 1e-5 parity bound
+    ref = json.load(open(os.path.join(golden_dir, "ref_gof.json")))
+    tab0 = sps.gof_table_from_device(st[0], labels)
+    tight = ref["dyny_tight"]                      # unmodified reference, odeint at rtol=1e-10
+    for var, row in zip(tight["index"], tight["values"]):
+        for col, val in zip(tight["columns"], row):
+            if col in sps.STATS_COLUMNS:
+                assert abs(tab0.loc[var, col] - val) <= 1e-5 * max(1.0, abs(val)), (var, col, tab0.loc[var, col], val)
+
+
+def test_sum_to_waterbody_on_device(cabi):
+    """sum_to_waterbody (model.py:851-900) as a device reduction over the flagged reaches for
+    every member and day, against the host implementation (pinned to the reference) on the 5-reach network."""
+    import torch
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from simplyp_b200.engine import Engine
+    from tests.golden.networks import network5_inputs
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    p, p_LU, p_SC, p_struc = network5_inputs(p, p_LU, p_SC, p_struc)
+    p_struc = p_struc.copy()
+    p_struc["In_final_flux?"] = [np.nan, np.nan, 1.0, 1.0, 1.0]
+    nc_types = pk.validate_land_use(p_SC, p["SC_list"])
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(6, seed=3)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    met = met.iloc[:120]
+    eng = Engine(0)
+    d_mem, d_sc = eng.to_device(member), eng.to_device(sc)
+    out, _ = eng.run(eng.to_device(pk.forcing_matrix(met)), d_mem, d_sc, topo.parent_offsets, topo.parent_ids, opt)
+    reaches = [i for i, s in enumerate(topo.sc_ids) if p_struc.loc[s, "In_final_flux?"] == 1]
+    wb = eng.sum_to_waterbody(out, d_mem, d_sc, reaches).cpu().numpy()
+    out_h = out.cpu().numpy()
+    for i in range(6):
+        R = {}
+        for k, SC in enumerate(topo.sc_ids):
+            _tc, R[SC] = spm.raw_to_frames(out_h[i, k], met.index, float(sc[i, k, pk.SC_INDEX["A_catch"]]),
+                                           p["Msoil_m2"], float(member[i, pk.MEMBER_INDEX["f_TDP"]]), nc_types[SC], None)
+        want = spm.sum_to_waterbody(p_struc, len(topo.sc_ids), R, float(member[i, pk.MEMBER_INDEX["f_TDP"]]))
+        for j, col in enumerate(Engine.WATERBODY_COLUMNS):
+            assert np.allclose(wb[i, :, j], want[col].to_numpy(), rtol=1e-12, atol=0), (i, col)
