@@ -87,7 +87,9 @@ enum {
   SIMPLYP_P_ERR_M3,        /* PP  */
   SIMPLYP_P_ERR_M4,        /* TP  */
   SIMPLYP_P_ERR_M5,        /* SRP */
-  SIMPLYP_NP_MEMBER = 40   /* row stride (2 spare) */
+  SIMPLYP_P_D_SNOW_0,      /* p['D_snow_0']  (read only when SimplypOptions.snow_on_device) */
+  SIMPLYP_P_F_DDSM,        /* p['f_DDSM']    (read only when SimplypOptions.snow_on_device) */
+  SIMPLYP_NP_MEMBER = 40   /* row stride */
 };
 
 /* Per-sub-catchment parameter vector: sc_params[Msc][S][SIMPLYP_NP_SC], Msc = 1 (shared by all
@@ -100,7 +102,10 @@ enum {
   SIMPLYP_NP_SC = 16       /* row stride (2 spare) */
 };
 
-/* forcing[D][SIMPLYP_NF]: P (rain+melt, mm/d; met_df['P']), PET (mm/d), day of year (1..366) , spare */
+/* forcing[D][SIMPLYP_NF]: P (rain+melt, mm/d; met_df['P']), PET (mm/d), day of year (1..366), T_air.
+ * With SimplypOptions.snow_on_device column 0 holds the raw met_df['Precipitation'] and column 3 met_df['T_air']
+ * (degrees C); P is then formed per member by the degree-day snow recursion of inputs.py:159-210 with that
+ * member's D_snow_0 and f_DDSM.  Otherwise column 3 is ignored. */
 #define SIMPLYP_NF 4
 
 /* Raw output row per (member, sub-catchment, day): out[M][S][D][SIMPLYP_NOUT].
@@ -178,7 +183,8 @@ typedef struct SimplypOptions {
                                 members over the lock-step warps (0 = default 8, < 0 = no pilot) */
   int32_t rank_stats;        /* calibration: also reduce Spearman's r (stores the simulated value of every observed
                                 day, M*V*D*8 bytes of workspace, and ranks them on the device afterwards) */
-  int32_t reserved[2];
+  int32_t snow_on_device;    /* 1: snow_hydrol_inputs (inputs.py:159-210) runs per member on the device (see forcing) */
+  int32_t reserved[1];
 } SimplypOptions;
 
 /* ---- entry points -------------------------------------------------------------------------- */

@@ -21,7 +21,7 @@ struct IO {
 extern "C" int steps_per_day(int M, int D, const double* forcing, const double* mp, const double* scp,
                              double rtol, double atol, uint16_t* steps) {
   ThreadOptions t; t.rtol = rtol; t.atol = atol; t.step_len = 1.0; t.max_steps_per_day = 5000;
-  t.dynamic_epc0 = 1; t.dynamic_erod = 1; t.run_mode_cal = 1; t.strict_quirks = 1;
+  t.snow_on_device = 0; t.dynamic_epc0 = 1; t.dynamic_erod = 1; t.run_mode_cal = 1; t.strict_quirks = 1;
 #pragma omp parallel for schedule(dynamic, 16)
   for (int m = 0; m < M; ++m) {
     ThreadCounters cnt; Cold c; RegStages ks;

@@ -36,7 +36,7 @@ class SimplypOptions(C.Structure):
                 ("max_steps_per_day", C.c_int32), ("dynamic_epc0", C.c_int32),
                 ("dynamic_erodibility", C.c_int32), ("run_mode_cal", C.c_int32), ("sc_qr0", C.c_int32),
                 ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("lanes_per_item", C.c_int32),
-                ("pilot_days", C.c_int32), ("rank_stats", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("pilot_days", C.c_int32), ("rank_stats", C.c_int32), ("snow_on_device", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class SimplypError(RuntimeError):

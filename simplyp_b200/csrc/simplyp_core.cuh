@@ -421,6 +421,18 @@ SP_HD void setup_thread(const double* mp, const double* sp, double A_qr0, int nc
   y[iPPr] = 0.0;
 }
 
+// snow_hydrol_inputs (inputs.py:159-210) for one day: precipitation falls as snow when T_air < 0, potential melt
+// f_DDSM*T_air (>= 0) is limited by the pack at the start of the day; returns P = rain + melt and advances the pack.
+SP_HD double snow_day(double precip, double t_air, double f_DDSM, double& depth) {
+  const double p_snow = (t_air < 0.0) ? precip : 0.0;            // :183-185
+  const double p_rain = precip - p_snow;                         // :186
+  double melt_pot = f_DDSM * (t_air - 0.0);                      // :188
+  if (melt_pot < 0.0) melt_pot = 0.0;                            // :191
+  const double melt = sp_min(melt_pot, depth);                   // :203
+  depth = depth + p_snow - melt;                                 // :204
+  return p_rain + melt;                                          // :208
+}
+
 // Values of a day that end up in the output row but are not states.
 struct DayAux {
   double Qq, C_cover_A, EPC0_A, EPC0_NC;

@@ -243,6 +243,13 @@ struct IOBase {
     E = f[1];
     doy = f[2];
   }
+  __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy, double& T_air) const {
+    const double* f = &ring->tiles[(day / FORC_TILE) % FORC_SLOTS][(day % FORC_TILE) * SIMPLYP_NF];
+    P = f[0];
+    E = f[1];
+    doy = f[2];
+    T_air = f[3];
+  }
 };
 
 // Full-output mode: parents' fluxes are read back from their output rows (columns Qr, Msus_kg/day,
@@ -834,6 +841,8 @@ int check_common(const SimplypDims* dims, const SimplypOptions* opt, const void*
     return fail(SIMPLYP_EINVAL, "rtol/atol/step_len must be positive%s");
   if (opt->lanes_per_item != 0 && opt->lanes_per_item != 1 && opt->lanes_per_item != 4)
     return fail(SIMPLYP_EINVAL, "lanes_per_item must be 0 (default), 1 or 4%s");
+  if (opt->snow_on_device && opt->lanes_per_item == 1)
+    return fail(SIMPLYP_EINVAL, "snow_on_device needs the quad kernel (lanes_per_item 0 or 4)%s");
   return SIMPLYP_OK;
 }
 
@@ -843,6 +852,7 @@ ThreadOptions make_topt(const SimplypOptions& o) {
   t.max_steps_per_day = o.max_steps_per_day > 0 ? o.max_steps_per_day : 5000;
   t.dynamic_epc0 = o.dynamic_epc0; t.dynamic_erod = o.dynamic_erodibility;
   t.run_mode_cal = o.run_mode_cal; t.strict_quirks = o.strict_quirks;
+  t.snow_on_device = o.snow_on_device;
   return t;
 }
 

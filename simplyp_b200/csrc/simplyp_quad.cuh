@@ -243,7 +243,7 @@ static_assert(sizeof(QuadMem) == 57 * sizeof(double), "QuadMem: odd double strid
 
 // IO policy concept of the quad program (all calls are made by every lane of the quad unless stated):
 //   void wait(int day);                          // block until forcing and upstream inputs of `day` exist
-//   void forcing(int day, double& P, double& E, double& doy);
+//   void forcing(int day, double& P, double& E, double& doy, double& T_air);
 //   void upstream(int day, double (&us)[4]);
 //   bool wants_vr();
 //   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
@@ -270,6 +270,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   }
   unsigned n_steps = 0, n_rej = 0;
   int status = 0;
+  double snow_depth = mp[SIMPLYP_P_D_SNOW_0];       // only used with snow_on_device
   const double T1 = opt.step_len;
   double hstep = 0.05 * T1;
 
@@ -278,8 +279,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     io.wait(day);
     {
       Hot h = qm.h;
-      double P, E, doy, us[4];
-      io.forcing(day, P, E, doy);
+      double P, E, doy, T_air, us[4];
+      io.forcing(day, P, E, doy, T_air);
+      if (opt.snow_on_device) P = snow_day(P, T_air, mp[SIMPLYP_P_F_DDSM], snow_depth);
       io.upstream(day, us);
       DayAux aux;
       begin_day(mp, sp, qm.c, qm.fl, opt.dynamic_epc0, opt.dynamic_erod, P, E, doy, us, h, aux);

@@ -19,6 +19,7 @@ struct ThreadOptions {
   double rtol, atol, step_len;
   int max_steps_per_day;
   int dynamic_epc0, dynamic_erod, run_mode_cal, strict_quirks;
+  int snow_on_device;   // quad kernel only: forcing carries raw precipitation and T_air, snow is a per-member scan
 };
 
 struct ThreadCounters {

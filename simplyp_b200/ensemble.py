@@ -115,8 +115,13 @@ def all_gather_stats(local_stats, n_members, group=None):
 
 
 def calibrate_ensemble(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, obs_dict, samples,
-                       variables=("Q", "TDP"), step_len=1.0, rtol=None, atol=None, engine=None, gather=True):
+                       variables=("Q", "TDP"), step_len=1.0, rtol=None, atol=None, engine=None, gather=True,
+                       snow_on_device=False, rank_stats=False):
     """Fused-statistics run of an ensemble; this rank integrates its shard and (optionally) all-gathers.
+
+    ``snow_on_device``: ``met_df`` carries the raw ``Precipitation`` and ``T_air``; the degree-day snow module
+    (reference ``inputs.py:159-210``) runs per member on the device, so ``D_snow_0`` and ``f_DDSM`` may be sampled.
+    ``rank_stats``: also reduce Spearman's r (the whole table of ``goodness_of_fit_stats``).
 
     Returns ``(stats [M][V][8] torch tensor on the device, labels [(reach, variable)], diag)``.
     """
@@ -131,13 +136,15 @@ def calibrate_ensemble(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, ob
     pk.check_erosion_windows(p)
     topo = pk.build_topology(p_struc, p["SC_list"])
     opt = make_options(p_SU, p, dynamic_options, topo, step_len, rtol, atol)
+    opt.snow_on_device = 1 if snow_on_device else 0
+    opt.rank_stats = 1 if rank_stats else 0
     member, sc = pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
     M = member.shape[0]
     rank, world = (dist.get_rank(), dist.get_world_size()) if (dist.is_available() and dist.is_initialized()) else (0, 1)
     lo, hi = shard_bounds(M, world, rank)
     obs, desc, labels = pk.obs_arrays(obs_dict, topo, met_df.index, variables)
     eng = engine or Engine()
-    d_forc = eng.to_device(pk.forcing_matrix(met_df))
+    d_forc = eng.to_device(pk.forcing_matrix(met_df, raw_snow=bool(snow_on_device)))
     d_mem = eng.to_device(member[lo:hi])
     d_sc = eng.to_device(sc if sc.shape[0] == 1 else sc[lo:hi])
     d_obs = eng.to_device(obs)

@@ -181,7 +181,7 @@ def run_simply_p(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, step_len
         "nst": int(diag[0, last, 0]), "nrej": int(diag[0, last, 1]), "nfe": int(diag[0, last, 2]),
         "status": int(diag[0, last, 3]),
         "message": "Integration successful." if status == 0 else "Integration finished with status bits %d" % status,
-        "rtol": opt.rtol, "atol": opt.atol, "method": "DOPRI5(4), sm_100a",
+        "rtol": opt.rtol, "atol": opt.atol, "method": "Tsitouras 5(4) embedded Runge-Kutta, quad kernel, sm_100a",
         "per_sc": {SC: {"nst": int(diag[0, i, 0]), "nrej": int(diag[0, i, 1]), "nfe": int(diag[0, i, 2]),
                         "status": int(diag[0, i, 3])} for i, SC in enumerate(sc_ids)},
     }

@@ -19,6 +19,7 @@ MEMBER_FIELDS = [
     "EPC0_init_mgl:A", "EPC0_init_mgl:S", "C_cover:A", "C_cover:S", "C_cover:IG",
     "C_measures:A", "C_measures:S", "C_measures:IG",
     "err_m:Q", "err_m:SS", "err_m:TDP", "err_m:PP", "err_m:TP", "err_m:SRP",
+    "D_snow_0", "f_DDSM",
 ]
 NP_MEMBER = 40
 MEMBER_INDEX = {name: i for i, name in enumerate(MEMBER_FIELDS)}
@@ -153,13 +154,18 @@ def sc_matrix(p_SC, sc_ids):
     return a
 
 
-def forcing_matrix(met_df):
-    """[D][4] array: P, PET, day-of-year, spare (reference ``model.py:497-498,550``)."""
+def forcing_matrix(met_df, raw_snow=False):
+    """[D][4] array: P, PET, day-of-year, T_air (reference ``model.py:497-498,550``).
+
+    ``raw_snow=True`` (for ``SimplypOptions.snow_on_device``): column 0 is the raw ``Precipitation`` and the
+    degree-day snow recursion (``inputs.py:159-210``) runs per member on the device."""
     D = len(met_df)
     f = np.zeros((D, NF))
-    f[:, 0] = met_df["P"].to_numpy(dtype="float64")
+    f[:, 0] = met_df["Precipitation" if raw_snow else "P"].to_numpy(dtype="float64")
     f[:, 1] = met_df["PET"].to_numpy(dtype="float64")
     f[:, 2] = met_df.index.dayofyear.to_numpy(dtype="float64")
+    if "T_air" in met_df.columns:
+        f[:, 3] = met_df["T_air"].to_numpy(dtype="float64")
     return f
 
 

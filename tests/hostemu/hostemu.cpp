@@ -20,6 +20,9 @@ struct HostIO {
   void forcing(int day, double& P, double& E, double& doy) const {
     P = fdata[4 * day]; E = fdata[4 * day + 1]; doy = fdata[4 * day + 2];
   }
+  void forcing(int day, double& P, double& E, double& doy, double& T_air) const {
+    P = fdata[4 * day]; E = fdata[4 * day + 1]; doy = fdata[4 * day + 2]; T_air = fdata[4 * day + 3];
+  }
   void upstream(int day, double (&us)[4]) const {
     us[0] = us[1] = us[2] = us[3] = 0.0;
     const double A_this = scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
@@ -56,6 +59,7 @@ extern "C" int hostemu_run(const SimplypDims* dims, const SimplypOptions* opt, c
   t.max_steps_per_day = opt->max_steps_per_day > 0 ? opt->max_steps_per_day : 5000;
   t.dynamic_epc0 = opt->dynamic_epc0; t.dynamic_erod = opt->dynamic_erodibility;
   t.run_mode_cal = opt->run_mode_cal; t.strict_quirks = opt->strict_quirks;
+  t.snow_on_device = opt->snow_on_device;
   for (int m = 0; m < M; ++m) {
     const double* mp = member_params + (size_t)m * SIMPLYP_NP_MEMBER;
     const double* scp = sc_params + (size_t)(Msc > 1 ? m : 0) * S * SIMPLYP_NP_SC;
@@ -90,6 +94,7 @@ extern "C" int hostemu_run_quad(const SimplypDims* dims, const SimplypOptions* o
   t.max_steps_per_day = opt->max_steps_per_day > 0 ? opt->max_steps_per_day : 5000;
   t.dynamic_epc0 = opt->dynamic_epc0; t.dynamic_erod = opt->dynamic_erodibility;
   t.run_mode_cal = opt->run_mode_cal; t.strict_quirks = opt->strict_quirks;
+  t.snow_on_device = opt->snow_on_device;
   for (int m = 0; m < M; ++m) {
     const double* mp = member_params + (size_t)m * SIMPLYP_NP_MEMBER;
     const double* scp = sc_params + (size_t)(Msc > 1 ? m : 0) * S * SIMPLYP_NP_SC;

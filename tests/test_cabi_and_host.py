@@ -73,7 +73,7 @@ def test_packing_layout_matches_header():
     header = open(os.path.join(ROOT, "include", "simplyp_b200.h")).read()
     body = header[header.index("SIMPLYP_P_F_QUICK = 0"):header.index("SIMPLYP_NP_MEMBER = ")]
     names = re.findall(r"SIMPLYP_P_([A-Z0-9_]+)", body)
-    assert len(names) == len(pk.MEMBER_FIELDS) == 38
+    assert len(names) == len(pk.MEMBER_FIELDS) == 40
     assert int(re.search(r"SIMPLYP_NP_MEMBER = (\d+)", header).group(1)) == pk.NP_MEMBER
     assert int(re.search(r"SIMPLYP_NP_SC = (\d+)", header).group(1)) == pk.NP_SC
     assert int(re.search(r"SIMPLYP_NOUT = (\d+)", header).group(1)) == pk.NOUT == len(pk.RAW_COLS)

@@ -381,3 +381,31 @@ def test_sum_to_waterbody_on_device(cabi):
         want = spm.sum_to_waterbody(p_struc, len(topo.sc_ids), R, float(member[i, pk.MEMBER_INDEX["f_TDP"]]))
         for j, col in enumerate(Engine.WATERBODY_COLUMNS):
             assert np.allclose(wb[i, :, j], want[col].to_numpy(), rtol=1e-12, atol=0), (i, col)
+
+
+def test_snow_parameters_in_the_ensemble(cabi):
+    """D_snow_0 and f_DDSM sampled per member, snow_hydrol_inputs (inputs.py:159-210) fused into
+    the kernel.  Every member must equal, bitwise, the run of that member alone on forcing pre-processed on the host
+    with its own snow parameters (the reference's order of operations)."""
+    from simplyp_b200 import ensemble as ens, inputs as spi, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load("2003-10-01", "2004-09-30", dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    ranges = dict(ens.TARLAND_RANGES)
+    ranges["D_snow_0"] = (0.0, 40.0)
+    ranges["f_DDSM"] = (1.0, 4.0)
+    samples = ens.latin_hypercube(48, ranges=ranges, seed=9)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    opt.snow_on_device = 1
+    raw = met[["T_air", "PET", "Precipitation"]]
+    out, dg = cabi.run_host(pk.forcing_matrix(raw, raw_snow=True), member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert np.all(np.isfinite(out)) and not np.any(dg[..., 3])
+    opt0 = spm.make_options(p_SU, p, dyn, topo)
+    melted = 0.0
+    for i in (0, 13, 47):
+        met_i = spi.snow_hydrol_inputs(samples["D_snow_0"][i], samples["f_DDSM"][i], raw)
+        melted += float(met_i["P_melt"].sum())
+        out_i, _ = cabi.run_host(pk.forcing_matrix(met_i), member[i:i + 1], sc[i:i + 1], topo.parent_offsets,
+                                 topo.parent_ids, opt0)
+        assert np.array_equal(out_i[0], out[i]), i
+    assert melted > 0

@@ -51,3 +51,24 @@ def test_table_exp_accuracy():
     got = hostemu.exp_tab(x)
     want = np.exp(x)
     assert np.max(np.abs(got - want) / want) < 5e-16      # 2 ulp
+
+
+def test_snow_on_device_equals_host_preprocessing(golden_dir):
+    """the degree-day snow recursion (inputs.py:159-210) fused into the day-start code with
+    per-member D_snow_0 / f_DDSM gives the same bits as running snow_hydrol_inputs on the host first."""
+    from simplyp_b200 import inputs as spi, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    for D0, fd in ((0.0, 2.74), (35.0, 1.3)):
+        p2 = p.copy(deep=True)
+        p2["D_snow_0"], p2["f_DDSM"] = D0, fd
+        met2 = spi.snow_hydrol_inputs(D0, fd, met[["T_air", "PET", "Precipitation"]])
+        member = pk.member_vector(p2, p_LU)[None]
+        sc = pk.sc_matrix(p_SC, topo.sc_ids)[None]
+        opt = spm.make_options(p_SU, p2, dyn, topo)
+        want, _ = hostemu.run_quad(pk.forcing_matrix(met2), member, sc, topo.parent_offsets, topo.parent_ids, opt)
+        opt.snow_on_device = 1
+        got, _ = hostemu.run_quad(pk.forcing_matrix(met2, raw_snow=True), member, sc, topo.parent_offsets,
+                                  topo.parent_ids, opt)
+        assert np.array_equal(got, want)
+        assert met2["P_melt"].sum() > 0          # the period really has snow
