@@ -668,19 +668,24 @@ SP_HD double step_factor(double en) {
 // The same controller on the MEAN SQUARE of the scaled error (no square root): 0.9*(en^2)^(-1/10) in [0.2, 5].
 // Device: fp32 lg2/ex2 with flush-to-zero and no range branches — an underflowing en^2 gives lg2 = -inf, hence
 // +inf, clamped to 5; an overflowing one gives 0, clamped to 0.2 (en^2 is never NaN here).
-SP_HD double step_factor_sq(double en2) {
+// `expo` = -1/(2p) for an estimate of order p-1 ... i.e. -0.1 for the 5(4) pair, -0.125 for Kaps-Rentrop 4(3).
+SP_HD double step_factor_sq(double en2, double expo = -0.1) {
 #if defined(__CUDA_ARCH__)
   float l, f;
   const float x = __double2float_rn(en2);
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
-  l *= -0.1f;
+  l *= (float)expo;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(l));
   return (double)fminf(fmaxf(0.9f * f, 0.2f), 5.0f);
 #else
-  if (!(en2 > 1e-38)) return 5.0;
+#ifndef SP_CTRL_SAFETY
+#define SP_CTRL_SAFETY 0.9
+#define SP_CTRL_MAXGROW 5.0
+#endif
+  if (!(en2 > 1e-38)) return SP_CTRL_MAXGROW;
   if (!(en2 < 1e38)) return 0.2;
-  const double f = 0.9 * exp(-0.1 * log(en2));
-  return sp_min(5.0, sp_max(0.2, f));
+  const double f = SP_CTRL_SAFETY * exp(expo * log(en2));
+  return sp_min(SP_CTRL_MAXGROW, sp_max(0.2, f));
 #endif
 }
 

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
 // instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
 enum { MODE_RUN = 0, MODE_CAL = 1, MODE_PILOT = 2 };
-template <int MODE, int MINB>
+template <int MODE, int MINB, bool STIFF>
 __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ unsigned s_vblock;
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   ThreadCounters cnt;
   if (MODE == MODE_PILOT) {
     PilotIO io(a, m, s, ring);
-    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
     if (valid && q.ql == 0) {
       const unsigned c = (unsigned)cnt.steps;
       a.cost[m] = c;
@@ -534,12 +534,12 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     return;
   } else if (MODE == MODE_CAL) {
     CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
-    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
     if (valid && q.ql == 0) io.finalise();
     cnt.status |= io.wait_status;
   } else {
     RunIO io(a, m, s, ring);
-    run_quad(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
     cnt.status |= io.wait_status;
   }
   if (a.diag && valid && q.ql == 0) {
@@ -891,9 +891,9 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   const int block = 128, qpb = block / 4;
   const long long grid = ((long long)dims.n_members + qpb - 1) / qpb;
   const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
-  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE_PILOT, 2><<<(unsigned)grid, block, smem, st>>>(p);
-  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE_PILOT, 3><<<(unsigned)grid, block, smem, st>>>(p);
-  else simplyp_quad_kernel<MODE_PILOT, 4><<<(unsigned)grid, block, smem, st>>>(p);
+  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE_PILOT, 2, false><<<(unsigned)grid, block, smem, st>>>(p);
+  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE_PILOT, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
+  else simplyp_quad_kernel<MODE_PILOT, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
   cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members);
   g_launches.fetch_add(3);
@@ -977,9 +977,12 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const int rc = order_members_by_cost(dims, opt, a, L, ws, st);
     if (rc) return rc;
     constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
-    if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2><<<(unsigned)grid, block, smem, st>>>(a);
-    else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3><<<(unsigned)grid, block, smem, st>>>(a);
-    else simplyp_quad_kernel<MODE, 4><<<(unsigned)grid, block, smem, st>>>(a);
+    // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of
+    // the 2-blocks-per-SM variant
+    if (S > 1) simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
+    else if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2, false><<<(unsigned)grid, block, smem, st>>>(a);
+    else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);
+    else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(a);
   }
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());

@@ -37,6 +37,19 @@
 
 #include "simplyp_thread.cuh"
 
+#ifndef SP_DAYSTART_FAC
+#define SP_DAYSTART_FAC 0.2   // day-start step = this x yesterday's last step (the forcing jumps at midnight);
+                              // 0.1 / 0.3 / 0.5 and "yesterday's first accepted step" all need more attempts
+                              // (scripts/controller_exp.py)
+#endif
+#ifndef SP_STIFF_RATE
+#define SP_STIFF_RATE 300.0   // reach rate constant Qr/((1-b_Q) Vr) per day above which a day is integrated by the
+                              // Rosenbrock path (the explicit pair needs > ~100 attempts per day there)
+#endif
+#ifndef SP_ROS_TOL_SCALE
+#define SP_ROS_TOL_SCALE 10.0 // Kaps-Rentrop's 3rd-order estimate is conservative: at 10x the tolerance its global error is
+                              // still below the explicit pair's (build/exp prototype: 1.2e-8 vs 3.6e-8 at rtol 1e-7)
+#endif
 #ifndef SP_SOIL_ERR_WEIGHT
 #define SP_SOIL_ERR_WEIGHT 1000.0
 #endif
@@ -56,12 +69,13 @@ inline V4 v4_splat(double x) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = x; ret
 // elementary operations on T (double on the device, V4 in the host harness)
 SP_HD double qfma(double a, double b, double c) { return fma(a, b, c); }
 SP_HD double qgate(double u) { return gate(u); }
+SP_HD double qclamp01(double u) { return sp_clamp01(u); }
 SP_HD double qrcp(double x) { return sp_rcp(x); }
 SP_HD double qrcp_fast(double x) { return sp_rcp_fast(x); }
 SP_HD double qabs(double x) { return fabs(x); }
 SP_HD double qmax(double a, double b) { return sp_max(a, b); }
 #define SP_V4_MAP1(name, f) inline V4 name(const V4& a) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = f(a.v[l]); return r; }
-SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
+SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qclamp01, sp_clamp01) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
 SP_V4_MAP1(qabs, fabs)
 #undef SP_V4_MAP1
 inline V4 qmax(const V4& a, const V4& b) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = sp_max(a.v[l], b.v[l]); return r; }
@@ -231,6 +245,160 @@ SP_HD double quad_attempt(const Q& q, const QuadCoef<Q>& c, const QuadState<Q>& 
   return (en2 == en2) ? en2 : INFINITY;   // NaN -> reject
 }
 
+// ------------------------------------------------------------------------------------------ stiff reaches
+// In a large network a main-stem reach carries the runoff of thousands of km2 over its own small area; its rate
+// constant Qr/((1-b_Q) Vr) then reaches 1e3 per day and the explicit pair becomes stability-bound (hundreds of
+// attempts per day).  LSODA switches to BDF there (model.py:640); this path switches, per item and per day, to a
+// linearly-implicit (Rosenbrock) method: Kaps-Rentrop 4(3) with Shampine's parameters (4 stages, 3 RHS
+// evaluations, L-stable-ish, embedded 3rd-order error estimate), with the EXACT Jacobian of ode_f.
+// The Jacobian is block lower-triangular in the order (VsA, VsS) -> Vg -> (u, Vr) -> (Msus, TDPr, PPr) -> the four
+// quadratures, so (I/(gamma h) - J) g = rhs is solved by forward substitution: lanes 0 and 1 divide, lane 2 divides
+// after receiving their results, lane 3 solves a 2x2 system, lanes 0-2 then finish their in-stream mass and every
+// lane its quadrature — five quad broadcasts per solve, no pivoting, no matrix in memory.
+namespace ros {
+constexpr double GAM = 0.5;
+constexpr double A21 = 2.0, A31 = 48.0 / 25.0, A32 = 6.0 / 25.0;
+constexpr double C21 = -8.0, C31 = 372.0 / 25.0, C32 = 12.0 / 5.0, C41 = -112.0 / 125.0, C42 = -54.0 / 125.0, C43 = -2.0 / 5.0;
+constexpr double B1 = 19.0 / 9.0, B2 = 0.5, B3 = 25.0 / 108.0, B4 = 125.0 / 108.0;
+constexpr double E1 = 17.0 / 54.0, E2 = 7.0 / 36.0, E3 = 0.0, E4 = 125.0 / 108.0;
+}  // namespace ros
+
+// Lane-local entries of the Jacobian of ode_f at one state (d = derivative of the row's component).
+template <class Q>
+struct QuadJac {
+  using T = typename Q::T;
+  T dAA;                  // slot A diagonal (lane 3: d(du)/du)
+  T jA1, jA2, jA3;        // slot A row: d/dVsA, d/dVsS, d/dVg   (zero where the column is the row itself or later)
+  T jB1, jB2, jB3;        // slot B row: d/dVsA, d/dVsS, d/dVg
+  T jB4, jB5, dBB;        // slot B row: d/du, d/dVr, diagonal   (lane 3 = Vr row: jB4 = -Qr, jB5 = dBB = 0)
+  T jC1, jC2, jC3;        // accumulator row: d/d(own slot B), d/du, d/dVr
+  T jUV;                  // lane 3: d(du)/dVr
+};
+
+// ode_f and its Jacobian at (yA, yB): returns the derivatives like quad_rhs and fills J.
+template <class Q>
+SP_HD void quad_rhs_jac(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, const typename Q::T& yB,
+                        typename Q::T& dA, typename Q::T& dB, typename Q::T& dacc, typename Q::T& e, QuadJac<Q>& J) {
+  using T = typename Q::T;
+  const T u = q.bcast(yA, 3);
+  const T rV = qrcp(q.bcast(yB, 3));
+  e = q.exp(qfma(c.eY, yA, c.eU * u));
+  const T w = qfma(c.p1, yA, c.p0);
+  const T wc = qclamp01(w);
+  const T fw = wc * wc * (3.0 - 2.0 * wc);
+  const T G = qfma(fw * w, c.g1, c.g0);
+  const T dG = (c.g1 * c.p1) * qfma(w * 6.0, wc * (1.0 - wc), fw);          // dG/d(own slot A)
+  const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
+  const T dGA = q.bcast(dG, 0), dGS = q.bcast(dG, 1), dGg = q.bcast(dG, 2);
+  const T qk = q.bcast(e, 2), Qr = q.bcast(e, 3);
+  const T L = (qfma(c.aE, e, c.a0) + qfma(c.aSA, QsA, c.aSS * QsS)) + qfma(c.aG, Qg, c.aR * Qr);
+  const T r = Qr * rV;
+  const T out = yB * r;
+  const T src = qfma(c.bK, qk, c.b0) + qfma(c.bSA, QsA, qfma(c.bSS, QsS, c.bG * Qg));
+  const T mult = qfma(rV, c.mA, c.m0);
+  dA = L * mult;
+  dB = src - out;
+  dacc = out;
+  // slot A: lanes 0,1 depend on themselves only; lane 2 (Vg) on VsA, VsS, itself; lane 3 (u) on all of them, u, Vr
+  const T up = q.pick(0.0, 0.0, 1.0, 1.0), up3 = q.pick(0.0, 0.0, 0.0, 1.0);
+  const T own = q.pick(-1.0, -1.0, -1.0, 0.0);                                 // coefficient of the own gated flow
+  J.dAA = (qfma(c.aE * c.eY, e, own * dG) + c.aR * Qr) * mult;
+  J.jA1 = up * c.aSA * dGA * mult;
+  J.jA2 = up * c.aSS * dGS * mult;
+  J.jA3 = up3 * c.aG * dGg * mult;
+  J.jUV = (0.0 - dA) * rV;                                                     // lane 3: d(net m)/dVr, m = mA/Vr
+  // slot B: in-stream masses (lanes 0-2), Vr (lane 3)
+  J.jB1 = c.bSA * dGA;
+  J.jB2 = c.bSS * dGS;
+  J.jB3 = c.bG * dGg;
+  J.jB4 = qfma(c.bK * q.bcast(c.eU, 2), qk, 0.0 - out);                        // d/du: k_M bK Qr^k_M - yB r (lane 3: -Qr)
+  J.jB5 = q.sel3(q.splat(0.0), out * rV);                                      // d/dVr: yB r / Vr
+  J.dBB = q.sel3(q.splat(0.0), 0.0 - r);
+  // accumulators: d(yB r) (lane 3: dQr = Qr du)
+  J.jC1 = q.sel3(q.splat(0.0), r);
+  J.jC2 = out;
+  J.jC3 = q.sel3(q.splat(0.0), (0.0 - out) * rV);
+}
+
+// Factors of (I/(gamma h) - J) that depend on the step size.
+template <class Q>
+struct QuadLU {
+  using T = typename Q::T;
+  T m11, m12, m21, m22;   // lanes 0-2: m11 = 1/(d - dAA), others 0; lane 3: inverse of the (u, Vr) 2x2 block
+  T idB;                  // lanes 0-2: 1/(d - dBB)
+  double gh;              // gamma h = 1/d
+};
+
+template <class Q>
+SP_HD void quad_factor(const Q& q, const QuadJac<Q>& J, double hh, QuadLU<Q>& F) {
+  using T = typename Q::T;
+  const double d = 1.0 / (ros::GAM * hh);
+  F.gh = ros::GAM * hh;
+  const T a = d - J.dAA;
+  // lane 3: [a, -jUV; -jB4, d]^-1 = 1/det [d, jUV; jB4, a]
+  const T det = q.sel3(a * d - J.jUV * J.jB4, a);
+  const T idet = qrcp(det);
+  F.m11 = q.sel3(d * idet, idet);
+  F.m12 = q.sel3(J.jUV * idet, q.splat(0.0));
+  F.m21 = q.sel3(J.jB4 * idet, q.splat(0.0));
+  F.m22 = q.sel3(a * idet, q.splat(0.0));
+  F.idB = qrcp(d - J.dBB);
+}
+
+// g = (I/(gamma h) - J)^-1 rhs for the lane's three components.
+template <class Q>
+SP_HD void quad_solve(const Q& q, const QuadJac<Q>& J, const QuadLU<Q>& F, const typename Q::T& rA, const typename Q::T& rB,
+                      const typename Q::T& rC, typename Q::T& gA, typename Q::T& gB, typename Q::T& gC) {
+  using T = typename Q::T;
+  const T g0 = rA * F.m11;                                   // final on lanes 0,1
+  const T gVsA = q.bcast(g0, 0), gVsS = q.bcast(g0, 1);
+  T t1 = qfma(J.jA1, gVsA, qfma(J.jA2, gVsS, rA));
+  T t2 = qfma(J.jB1, gVsA, qfma(J.jB2, gVsS, rB));
+  const T gVg = q.bcast(t1 * F.m11, 2);                      // final on lane 2
+  t1 = qfma(J.jA3, gVg, t1);
+  t2 = qfma(J.jB3, gVg, t2);
+  gA = qfma(F.m11, t1, F.m12 * t2);                          // lane 3: g_u ; lanes 0-2: their slot A
+  const T y = qfma(F.m21, t1, F.m22 * t2);                   // lane 3: g_Vr
+  const T gu = q.bcast(gA, 3), gV = q.bcast(y, 3);
+  gB = q.sel3(y, qfma(J.jB4, gu, qfma(J.jB5, gV, t2)) * F.idB);
+  gC = qfma(J.jC1, gB, qfma(J.jC2, gu, qfma(J.jC3, gV, rC))) * F.gh;
+}
+
+// One Kaps-Rentrop step attempt from s (its k1*, a1, e1 must hold ode_f at s, J the Jacobian there).
+// Returns the mean square of the scaled error estimate; the new state comes back in yn*.
+template <class Q>
+SP_HD double quad_attempt_ros(const Q& q, const QuadCoef<Q>& c, const QuadState<Q>& s, const QuadJac<Q>& J, double hh,
+                              double rtol, double atol, typename Q::T& ynA, typename Q::T& ynB, typename Q::T& accn) {
+  using namespace ros;
+  using T = typename Q::T;
+  QuadLU<Q> F;
+  quad_factor(q, J, hh, F);
+  const double ih = 1.0 / hh;
+  T g1A, g1B, g1C, g2A, g2B, g2C, g3A, g3B, g3C, g4A, g4B, g4C, fA, fB, fC, ee;
+  quad_solve(q, J, F, s.k1A, s.k1B, s.a1, g1A, g1B, g1C);
+  quad_rhs(q, c, qfma(A21, g1A, s.yA), qfma(A21, g1B, s.yB), fA, fB, fC, ee);
+  quad_solve(q, J, F, qfma(C21 * ih, g1A, fA), qfma(C21 * ih, g1B, fB), qfma(C21 * ih, g1C, fC), g2A, g2B, g2C);
+  quad_rhs(q, c, qfma(A32, g2A, qfma(A31, g1A, s.yA)), qfma(A32, g2B, qfma(A31, g1B, s.yB)), fA, fB, fC, ee);
+  quad_solve(q, J, F, qfma(C32 * ih, g2A, qfma(C31 * ih, g1A, fA)), qfma(C32 * ih, g2B, qfma(C31 * ih, g1B, fB)),
+             qfma(C32 * ih, g2C, qfma(C31 * ih, g1C, fC)), g3A, g3B, g3C);
+  quad_solve(q, J, F, qfma(C43 * ih, g3A, qfma(C42 * ih, g2A, qfma(C41 * ih, g1A, fA))),
+             qfma(C43 * ih, g3B, qfma(C42 * ih, g2B, qfma(C41 * ih, g1B, fB))),
+             qfma(C43 * ih, g3C, qfma(C42 * ih, g2C, qfma(C41 * ih, g1C, fC))), g4A, g4B, g4C);
+  ynA = qfma(B4, g4A, qfma(B3, g3A, qfma(B2, g2A, qfma(B1, g1A, s.yA))));
+  ynB = qfma(B4, g4B, qfma(B3, g3B, qfma(B2, g2B, qfma(B1, g1B, s.yB))));
+  accn = qfma(B4, g4C, qfma(B3, g3C, qfma(B2, g2C, qfma(B1, g1C, s.acc))));
+  const T eA = qfma(E4, g4A, qfma(E2, g2A, E1 * g1A));       // E3 = 0
+  const T eB = qfma(E4, g4B, qfma(E2, g2B, E1 * g1B));
+  const T ec = qfma(E4, g4C, qfma(E2, g2C, E1 * g1C));
+  const T sA = q.sel3(s.e1, qmax(qabs(s.yA), qabs(ynA)));    // u is weighted like Qr (Qr at the start of the step)
+  const T wA = q.sel3(s.e1, q.pick(SP_SOIL_ERR_WEIGHT, SP_SOIL_ERR_WEIGHT, 1.0, 1.0));
+  const T qA = (eA * wA) * qrcp_fast(qfma(rtol, sA, atol));
+  const T qB = eB * qrcp_fast(qfma(rtol, qmax(qabs(s.yB), qabs(ynB)), atol));
+  const T qc = ec * qrcp_fast(qfma(rtol, qmax(qabs(s.acc), qabs(accn)), atol));
+  const double en2 = q.first(q.sum(qfma(qA, qA, qfma(qB, qB, qc * qc)))) * (1.0 / 12.0);
+  return (en2 == en2) ? en2 : INFINITY;
+}
+
 // Day-boundary state of a quad kept outside the registers (device: shared memory, one per quad).
 struct QuadMem {
   Hot h;
@@ -251,7 +419,9 @@ static_assert(sizeof(QuadMem) == 57 * sizeof(double), "QuadMem: odd double strid
 //   void publish(int day);                       // leader only
 //
 // The whole record of one (member, sub-catchment) item: replaces model.py:491-724 for it.
-template <class Q, class IO>
+// STIFF compiles the Rosenbrock path in (networks); without it every day takes the explicit pair (ensembles of one
+// sub-catchment, where the reach rate constant stays below ~150 per day and the extra code would only cost registers).
+template <bool STIFF, class Q, class IO>
 SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0, int nc_last,
                     const ThreadOptions& opt, int n_days, bool valid, QuadMem& qm, IO& io, ThreadCounters& cnt) {
   using T = typename Q::T;
@@ -268,7 +438,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     if (q.leader()) { qm.h = h; qm.c = c; qm.fl = fl; }
     q.sync();
   }
-  unsigned n_steps = 0, n_rej = 0;
+  unsigned n_steps = 0, n_rej = 0, n_rhs = 0;
   int status = 0;
   double snow_depth = mp[SIMPLYP_P_D_SNOW_0];       // only used with snow_on_device
   const double T1 = opt.step_len;
@@ -290,20 +460,54 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       if (q.leader()) { qm.h = h; qm.aux = aux; }
     }
     s.acc = q.splat(0.0);                         // :618
-    quad_rhs(q, qc, s.yA, s.yB, s.k1A, s.k1B, s.a1, s.e1);
+    QuadJac<Q> J;
+    quad_rhs_jac(q, qc, s.yA, s.yB, s.k1A, s.k1B, s.a1, s.e1, J);
+    n_rhs += 1;
+    // reach rate constant -d(du/dt)/du = Qr/((1-b_Q) Vr), per day: stiff days go to the Rosenbrock path
+    const bool stiff = STIFF && (0.0 - q.first(q.bcast(J.dAA, 3))) > SP_STIFF_RATE;
+    bool jac_fresh = true;
     double t = 0.0;
     int day_steps = 0;
     bool grow_ok = true;
     bool active = true;
-    hstep = sp_min(hstep * 0.2, T1);              // the forcing jumps at midnight
+    hstep = sp_min(hstep * SP_DAYSTART_FAC, T1);  // the forcing jumps at midnight
 
     // ---- step loop: lock-step over the quads of a warp ------------------------------------------
     while (q.any(active)) {
       const double rem = T1 - t;
       const bool last = hstep * 1.0000001 >= rem;
       const double hh = active ? (last ? rem : hstep) : hstep;
-      T ynA, ynB, accn, k7A, k7B, a7, e7;
-      const double en2 = quad_attempt(q, qc, s, hh, opt.rtol, opt.atol, ynA, ynB, accn, k7A, k7B, a7, e7);
+      const bool do_rk = active && !stiff, do_ros = active && stiff;
+      T ynA, ynB, accn;
+      double en2 = 0.0, expo = -0.1;
+      if (!STIFF || q.any(do_rk) || !q.any(do_ros)) {
+        T k7A, k7B, a7, e7;
+        const double e2 = quad_attempt(q, qc, s, hh, opt.rtol, opt.atol, ynA, ynB, accn, k7A, k7B, a7, e7);
+        if (do_rk) {
+          en2 = e2;
+          n_rhs += 6;
+          if (e2 <= 1.0 || day_steps + 1 >= opt.max_steps_per_day || hh < 1e-12 * T1) {   // will be accepted below
+            s.k1A = k7A; s.k1B = k7B; s.a1 = a7; s.e1 = e7;
+          }
+        }
+      }
+      if (STIFF && q.any(do_ros)) {
+        if (q.any(do_ros && !jac_fresh)) {         // ode_f and its Jacobian at the state reached by the last step
+          T fA, fB, fC, e0;
+          QuadJac<Q> Jn;
+          quad_rhs_jac(q, qc, s.yA, s.yB, fA, fB, fC, e0, Jn);
+          if (do_ros && !jac_fresh) {
+            s.k1A = fA; s.k1B = fB; s.a1 = fC; s.e1 = e0;
+            J = Jn;
+            jac_fresh = true;
+            n_rhs += 1;
+          }
+        }
+        T rA, rB, rC;
+        const double e2 = quad_attempt_ros(q, qc, s, J, hh, opt.rtol * SP_ROS_TOL_SCALE, opt.atol * SP_ROS_TOL_SCALE,
+                                           rA, rB, rC);
+        if (do_ros) { en2 = e2; expo = -0.125; ynA = rA; ynB = rB; accn = rC; n_rhs += 2; }
+      }
       if (active) {
         n_steps += 1;
         day_steps += 1;
@@ -312,11 +516,11 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
           accept = true;                          // forward-progress guard
           status |= 1;
         }
-        double fac = step_factor_sq(en2);
+        double fac = step_factor_sq(en2, expo);
         if (accept) {
           t += hh;
           s.yA = ynA; s.yB = ynB; s.acc = accn;
-          s.k1A = k7A; s.k1B = k7B; s.a1 = a7; s.e1 = e7;
+          if (stiff) jac_fresh = false;           // (the explicit path took its FSAL derivative above)
           if (!grow_ok) fac = sp_min(fac, 1.0);
           grow_ok = true;
           const double hnew = hh * fac;
@@ -335,7 +539,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       double y[NL], yraw[NL], acc[NA], non[13];
       const double u_end = q.first(q.bcast(s.yA, 3));
       y[iVsA] = q.first(q.bcast(s.yA, 0)); y[iVsS] = q.first(q.bcast(s.yA, 1)); y[iVg] = q.first(q.bcast(s.yA, 2));
-      y[iQr] = q.first(q.bcast(s.e1, 3));                      // Qr = exp(u) from the accepted step's last stage
+      y[iQr] = sp_exp(u_end);
       y[iMsus] = q.first(q.bcast(s.yB, 0)); y[iTDPr] = q.first(q.bcast(s.yB, 1)); y[iPPr] = q.first(q.bcast(s.yB, 2));
       const double Vr = q.first(q.bcast(s.yB, 3));
       acc[1] = q.first(q.bcast(s.acc, 0)); acc[2] = q.first(q.bcast(s.acc, 1)); acc[3] = q.first(q.bcast(s.acc, 2));
@@ -365,7 +569,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   }
   cnt.steps = n_steps;
   cnt.rejected = n_rej;
-  cnt.rhs_evals = 6ll * n_steps + n_days;
+  cnt.rhs_evals = n_rhs;
   cnt.status = status;
   (void)Kf;
 }

@@ -107,7 +107,7 @@ extern "C" int hostemu_run_quad(const SimplypDims* dims, const SimplypOptions* o
       QuadHost4 q;
       QuadMem qm;
       ThreadCounters cnt;
-      run_quad(q, mp, scp + (size_t)s * SIMPLYP_NP_SC, A_qr0, nc_last, t, D, true, qm, io, cnt);
+      run_quad<true>(q, mp, scp + (size_t)s * SIMPLYP_NP_SC, A_qr0, nc_last, t, D, true, qm, io, cnt);
       if (diag) {
         int64_t* dg = diag + ((size_t)m * S + s) * SIMPLYP_NDIAG;
         dg[0] = cnt.steps; dg[1] = cnt.rejected; dg[2] = cnt.rhs_evals; dg[3] = cnt.status;

@@ -107,3 +107,24 @@ def check_ensemble_series(runner, golden_dir, members=None):
             assert e <= PARITY, (i, c, e)
     assert not np.any(diag[..., 3])
     return worst
+
+
+def check_stiff_chain(runner, area, n_days=45, max_steps_per_day=None):
+    """A stiff outlet reach (tests/golden/stiff_chain.py) against the oracle: LSODA at rtol=1e-10, which integrates
+    it with BDF.  Returns the outlet reach's step attempts per day."""
+    from oracle import simplyp_oracle as orc
+    from simplyp_b200 import tarland
+    from tests.golden.stiff_chain import stiff_chain_inputs
+    p_SU, dyn, p, p_LU, p_SC0, p_struc0, met, obs = tarland.load(dynamic="y")
+    p, p_SC, p_struc = stiff_chain_inputs(p, p_SC0[1], area)
+    met = met.iloc[:n_days]
+    TC, R, diag, met = run_single(runner, (p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs))
+    TCo, Ro, _Kf, _ = orc.run_simply_p(met, p_struc, p_SU, p_LU.copy(), p_SC.copy(), p, dyn, rtol=1e-10, atol=1e-13,
+                                       mxstep=500000)
+    for SC in (1, 2, 3):
+        assert_frames_close(TC[SC], R[SC], TCo[SC], Ro[SC], "stiff chain SC %d (area %g)" % (SC, area))
+    assert not np.any(diag[..., 3])
+    per_day = diag[0, 2, 0] / float(n_days)
+    if max_steps_per_day is not None:
+        assert per_day <= max_steps_per_day, per_day
+    return per_day

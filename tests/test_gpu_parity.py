@@ -409,3 +409,10 @@ def test_snow_parameters_in_the_ensemble(cabi):
                                  topo.parent_ids, opt0)
         assert np.array_equal(out_i[0], out[i]), i
     assert melted > 0
+
+
+@pytest.mark.parametrize("area", [0.05, 5.0])
+def test_stiff_reach_vs_oracle(cabi, area):
+    """The Rosenbrock path of the quad kernel (stiff main-stem-like reach) against LSODA/BDF at tight tolerance."""
+    per_day = parity.check_stiff_chain(cabi.run_host, area, max_steps_per_day=100)
+    assert per_day > 20

@@ -72,3 +72,12 @@ def test_snow_on_device_equals_host_preprocessing(golden_dir):
                                   topo.parent_ids, opt)
         assert np.array_equal(got, want)
         assert met2["P_melt"].sum() > 0          # the period really has snow
+
+
+@pytest.mark.parametrize("area", [0.05, 1.0, 5.0])
+def test_stiff_reach_takes_the_rosenbrock_path(area):
+    """Main-stem-like reach (flow 300 ... 32,000 mm/d over its own area): the quad program switches that reach to
+    Kaps-Rentrop 4(3) with the exact Jacobian; parity bound as everywhere, and far fewer attempts than the explicit
+    pair needs (one-thread-per-item program: 112 ... 690 per day)."""
+    per_day = parity.check_stiff_chain(hostemu.run_quad, area, max_steps_per_day=100)
+    assert per_day > 20
