@@ -458,6 +458,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       quad_daily_coef(q, h, qc);
       q.sync();                                   // everybody has read qm before the leader rewrites it
       if (q.leader()) { qm.h = h; qm.aux = aux; }
+      q.sync();                                   // ... and the end-of-day code of every lane sees the new values
     }
     s.acc = q.splat(0.0);                         // :618
     QuadJac<Q> J;
