@@ -18,15 +18,15 @@ for name, ins in funcs.items():
         if t.startswith("EXIT"):
             ins = ins[:i + 1]
             break
-    best = None   # the smallest backward-branch span that holds at least half of the function's shuffles
-    n_shfl = sum(1 for a, s in ins if "SHFL" in s)
+    best = None   # the smallest backward-branch span that holds at least 25 % of the function's DFMAs
+    n_shfl = sum(1 for a, s in ins if "DFMA" in s)
     for a, s in ins:
         m = re.search(r"\bBRA(?:\.\w+)*\s+(?:\w+,\s*)?(0x[0-9a-f]+)", s)
         if m:
             t = int(m.group(1), 16)
             if t < a:
-                k = sum(1 for b, s2 in ins if t <= b <= a and "SHFL" in s2)
-                if 2 * k >= n_shfl and (best is None or a - t < best[1] - best[0]):
+                k = sum(1 for b, s2 in ins if t <= b <= a and "DFMA" in s2)
+                if 4 * k >= n_shfl and (best is None or a - t < best[1] - best[0]):
                     best = (t, a)
     body = [s for a, s in ins if best and best[0] <= a <= best[1]]
     c = collections.Counter()
