@@ -199,10 +199,12 @@ struct IOBase {
     return true;
   }
   // quad program: block (the whole warp) until forcing and upstream inputs of `day` exist
-  // A watchdog (about 4 s of SM clock) turns a wait that can never end (a bug, or a launch that violates the
-  // dispatch-order argument) into status bit 2 instead of a hung device.
+  // A watchdog (2^37 cycles, about 70 s of SM clock) turns a wait that can never end (a bug, or a launch that
+  // violates the dispatch-order argument) into status bit 2 instead of a hung device.  A legitimate wait is short:
+  // the parents of a reach were dispatched earlier and are resident or finished, so a warp of topological level L
+  // waits at most about L day-times at the start of the run (a chain of 10^5 reaches: ~3 s) and a day-time after.
   __device__ __forceinline__ void wait(int day) {
-    const long long limit = 8000000000ll;
+    const long long limit = 1ll << 37;
     const long long t0 = clock64();
     bool ok = true;
     while (ok && !forcing_ready_warp(day)) ok = (clock64() - t0) < limit;
