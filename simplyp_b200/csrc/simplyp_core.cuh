@@ -113,7 +113,9 @@ SP_HD double sp_ll2d(long long b) {
 SP_HD double sp_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 good bits
+  // volatile: keeps the MUFU where the source puts it relative to the quad broadcasts (ptxas otherwise sinks the
+  // whole reciprocal chain behind the exponential and puts it on the critical path of the RHS evaluation)
+  asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 good bits
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
@@ -174,39 +176,52 @@ SP_HD double sp_exp_core(double x) {
   return sp_ll2d(sp_d2ll(p) + ((long long)kf << 52));
 }
 
-// Table-driven e^x for the quad kernel: x = (32 m + j) ln2/32 + r with |r| <= ln2/64, e^x = 2^m * 2^(j/32) * e^r.
+// Table-driven e^x for the quad kernel: x = (64 m + j) ln2/64 + r with |r| <= ln2/128, e^x = 2^m * 2^(j/64) * e^r.
 // The reduction uses the 1.5*2^52 trick (the integer lands in the low word of the sum: no FRND/F2I), e^r is a
-// degree-6 polynomial (remainder r^7/7! < 4e-18) and 2^(j/32) comes from a 32-entry table (`tab`: shared
-// memory on the device, kExp2Tab on the host).  |x| < 700, no range check.  Accuracy ~1.5 ulp.
+// degree-5 polynomial (remainder r^6/6! < 4e-17) and 2^(j/64) comes from a 64-entry table (`tab`: shared memory on
+// the device, kExp2Tab on the host).  The table entry is scaled by 2^m with integer arithmetic while the
+// polynomial is still being evaluated, so one multiply finishes the function.  |x| < 700, no range check.
+// Accuracy ~1.5 ulp.
+constexpr int EXP_TAB = 64;
 SP_CONST double kExpT[12] = {
-    46.16624130844683,      // 32/ln2
-    -0.02166084937925916,     // -ln2/32, high part (22 trailing zero bits: k*hi is exact for |k| < 2^22)
-    -1.3239129268154012e-11,  // -ln2/32, low part
+    92.33248261689366,      // 64/ln2
+    -0.01083042468962958,    // -ln2/64, high part (22 trailing zero bits: k*hi is exact for |k| < 2^22)
+    -6.619564634077006e-12,  // -ln2/64, low part
     6755399441055744.0,      // 1.5*2^52
-    0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 0.0, 0.0, 0.0};
-// 2^(j/32), j = 0..31, correctly rounded (generated with 60-digit decimal arithmetic)
-SP_CONST double kExp2Tab[32] = {
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
-    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
-    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
-    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
-    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
-    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
-    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
-    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
-SP_HD double sp_exp_tab(double x, const double* tab) {
-  const double t = fma(x, kExpT[0], kExpT[3]);
+    0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 0.0, 0.0, 0.0, 0.0};
+// 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic)
+SP_CONST double kExp2Tab[EXP_TAB] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+// `t` = x*(64/ln2) + 1.5*2^52 may be formed by the caller.
+SP_HD double sp_exp_tab_pre(double x, double t, const double* tab) {
   const double kf = t - kExpT[3];
   const int ki = (int)(unsigned)(sp_d2ll(t) & 0xffffffffLL);      // two's-complement integer in the low word
+  // 2^(j/64) * 2^m: exponent field of the table entry plus m (off the critical path)
+  const double sc = sp_ll2d(sp_d2ll(tab[ki & (EXP_TAB - 1)]) + ((long long)(ki >> 6) << 52));
   double r = fma(kf, kExpT[1], x);
   r = fma(kf, kExpT[2], r);
   const double r2 = r * r;
-  const double c = fma(r2, kExpT[8], fma(r, kExpT[7], kExpT[6]));
+  const double c = fma(r, kExpT[7], kExpT[6]);
   const double b = fma(r, kExpT[5], kExpT[4]);
   const double p = fma(r2, fma(r2, c, b), 1.0 + r);
-  const double v = p * tab[ki & 31];
-  return sp_ll2d(sp_d2ll(v) + ((long long)(ki >> 5) << 52));
+  return p * sc;
 }
+SP_HD double sp_exp_tab(double x, const double* tab) { return sp_exp_tab_pre(x, fma(x, kExpT[0], kExpT[3]), tab); }
 
 // Range-checked variant for the once-a-day algebra: arguments are clamped to [-700, 700]
 // (e^-700 ~ 1e-304 stands in for an underflow to 0).

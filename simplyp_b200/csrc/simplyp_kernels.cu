@@ -466,8 +466,8 @@ template <int MODE, int MINB, bool STIFF>
 __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ unsigned s_vblock;
-  __shared__ double s_exp2tab[32];
-  if (threadIdx.x < 32) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
+  __shared__ double s_exp2tab[EXP_TAB];
+  if (threadIdx.x < EXP_TAB) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
   unsigned vblock = blockIdx.x;
   if (a.ticket != nullptr) {
     if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);

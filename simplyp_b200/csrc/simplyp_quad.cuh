@@ -180,19 +180,25 @@ template <class Q>
 SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, const typename Q::T& yB,
                     typename Q::T& dA, typename Q::T& dB, typename Q::T& dacc, typename Q::T& e) {
   using T = typename Q::T;
-  const T u = q.bcast(yA, 3);
-  const T rV = qrcp(q.bcast(yB, 3));
-  e = q.exp(qfma(c.eY, yA, c.eU * u));
+  // Source order = intended issue order (ptxas keeps independent chains roughly where they are written): the gated
+  // flows depend on the lane's own state only, so they are computed and broadcast FIRST; the exponential, which
+  // waits for the broadcast of u, then has only its own two broadcasts behind it.
   const T w = qfma(c.p1, yA, c.p0);
   const T G = qfma(qgate(w) * w, c.g1, c.g0);
+  const T u = q.bcast(yA, 3);
+  const T Vr = q.bcast(yB, 3);
+  const T rV = qrcp(Vr);
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
+  e = q.exp(qfma(c.eY, yA, c.eU * u));
+  const T gsum = qfma(c.aSA, QsA, c.aSS * QsS) + c.aG * Qg;                  // ready before the exponential
+  const T src0 = qfma(c.bSA, QsA, qfma(c.bSS, QsS, qfma(c.bG, Qg, c.b0)));
+  const T mult = qfma(rV, c.mA, c.m0);
   const T qk = q.bcast(e, 2), Qr = q.bcast(e, 3);
-  const T L = (qfma(c.aE, e, c.a0) + qfma(c.aSA, QsA, c.aSS * QsS)) + qfma(c.aG, Qg, c.aR * Qr);
+  const T L = (qfma(c.aE, e, c.a0) + gsum) + c.aR * Qr;
   const T r = Qr * rV;                       // Qr/Vr
   const T out = yB * r;                      // outflow of the lane's in-stream mass (:145,147,166,168,178,180)
-  const T src = qfma(c.bK, qk, c.b0) + qfma(c.bSA, QsA, qfma(c.bSS, QsS, c.bG * Qg));
-  dA = L * qfma(rV, c.mA, c.m0);             // lane 3: du/dt = net/((1-b_Q) Vr)
-  dB = src - out;                            // lane 3: out = Vr*Qr/Vr = Qr, src = net + Qr -> dVr/dt = net (:131)
+  dA = L * mult;                             // lane 3: du/dt = net/((1-b_Q) Vr)
+  dB = qfma(c.bK, qk, src0) - out;           // lane 3: out = Vr*Qr/Vr = Qr, src = net + Qr -> dVr/dt = net (:131)
   dacc = out;                                // lane 3: dQr_av/dt = Qr (:132)
 }
 
