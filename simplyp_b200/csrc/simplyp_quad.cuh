@@ -50,6 +50,10 @@
 #define SP_ROS_TOL_SCALE 10.0 // Kaps-Rentrop's 3rd-order estimate is conservative: at 10x the tolerance its global error is
                               // still below the explicit pair's (build/exp prototype: 1.2e-8 vs 3.6e-8 at rtol 1e-7)
 #endif
+#ifndef SP_W_B
+#define SP_W_B 1.0     // weight of the slot-B (in-stream masses, Vr) terms of the error norm
+#define SP_W_ACC 1.0   // weight of the daily accumulators
+#endif
 #ifndef SP_SOIL_ERR_WEIGHT
 #define SP_SOIL_ERR_WEIGHT 1000.0
 #endif
@@ -245,8 +249,8 @@ SP_HD double quad_attempt(const Q& q, const QuadCoef<Q>& c, const QuadState<Q>& 
   const T sA = q.sel3(Qmax, qmax(qabs(s.yA), qabs(ynA)));
   const T wA = q.sel3(Qmax, q.pick(SP_SOIL_ERR_WEIGHT, SP_SOIL_ERR_WEIGHT, 1.0, 1.0));
   const T qA = (eA * wA) * qrcp_fast(qfma(rtol, sA, atol));
-  const T qB = eB * qrcp_fast(qfma(rtol, qmax(qabs(s.yB), qabs(ynB)), atol));
-  const T qc = ec * qrcp_fast(qfma(rtol, qmax(qabs(s.acc), qabs(accn)), atol));
+  const T qB = (eB * SP_W_B) * qrcp_fast(qfma(rtol, qmax(qabs(s.yB), qabs(ynB)), atol));
+  const T qc = (ec * SP_W_ACC) * qrcp_fast(qfma(rtol, qmax(qabs(s.acc), qabs(accn)), atol));
   const double en2 = q.first(q.sum(qfma(qA, qA, qfma(qB, qB, qc * qc)))) * (1.0 / 12.0);
   return (en2 == en2) ? en2 : INFINITY;   // NaN -> reject
 }
