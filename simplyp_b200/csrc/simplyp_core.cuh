@@ -75,7 +75,7 @@ struct Cold {
   double tdp_fixed;      // TDPeff (kg/day)
   // soil-P state carried between days (:426-446, :684-715)
   double PlabA, TDPsA, PlabNC, TDPsNC, concA, concNC;
-  double spare;
+  double T_g;            // groundwater time constant (the floor resets Vg = Qg*T_g, :670)
 };
 static_assert(sizeof(Cold) == 25 * sizeof(double), "Cold must stay 25 doubles (bank-conflict-free stride)");
 
@@ -313,7 +313,7 @@ SP_HD double reach_volume(const Hot& c, double Qr) { return Qr / (c.cR * sp_exp(
 SP_HD void soilp_update(double pnet, double KfMsoil, double EPC0, double Qs, double Qq, double Vs,
                         double& TDPs, double& Plab) {
   const double a = pnet + KfMsoil * EPC0;
-  const double iVs = 1.0 / Vs;
+  const double iVs = sp_rcp(Vs);
   const double b = (KfMsoil + Qs + Qq) * iVs;
   const double ib = sp_rcp(b);
   const double ab = a * ib;
@@ -335,10 +335,11 @@ SP_HD double season_cover(double doy, double mid, double C_cover) {
   const double k = doy - start;
   const bool inside = (k >= 0.0) && (doy < end) && (k == floor(k));
   if (inside) {
-    if (doy < mid) return C_cover + (1.0 - C_cover) * (doy - start) / (mid - start);
-    return 1.0 + (C_cover - 1.0) * (doy - mid) / (end - mid);
+    // lin_interp (helper_functions.py:77) over windows that are exactly half = 30 days wide
+    if (doy < mid) return C_cover + (1.0 - C_cover) * (doy - start) * (1.0 / half);
+    return 1.0 + (C_cover - 1.0) * (doy - mid) * (1.0 / half);
   }
-  return C_cover - (60.0 * (1.0 - C_cover) / (2.0 * (365.0 - 60.0)));
+  return C_cover - (1.0 - C_cover) * (60.0 / (2.0 * (365.0 - 60.0)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -409,7 +410,7 @@ SP_HD void setup_thread(const double* mp, const double* sp, double A_qr0, int nc
   c.pp3 = fS * (1.0 - fNCS) * eS * c.P_inactive;                 // :173
   c.pp4 = fAr * fNCAr * baseA;                                   // :174
   c.pp5 = fIG * fNCIG * eIG + fS * fNCS * eS;                    // :175-176
-  c.spare = 0.0;
+  c.T_g = mp[SIMPLYP_P_T_G];
   c.tdpA = fA * (1.0 - fNCA);                                    // :155,159
   c.tdpNC = fA * fNCA + fS * fNCS;                               // :156-157,160-161
   double TDPeff = sp[SIMPLYP_SC_TDPEFF];
@@ -477,8 +478,9 @@ SP_HD void begin_day(const double* mp, const double* sp, const Cold& c, const Fl
   // EPC0 (:600-611)
   double EPC0_A, EPC0_NC;
   if (dynamic_epc0) {
-    EPC0_A = sp_max(c.PlabA / c.KfMsoil, 0.0);
-    EPC0_NC = sp_max(c.PlabNC / c.KfMsoil, 0.0);
+    const double iKM = sp_rcp(c.KfMsoil);
+    EPC0_A = sp_max(c.PlabA * iKM, 0.0);
+    EPC0_NC = sp_max(c.PlabNC * iKM, 0.0);
   } else {
     EPC0_A = mp[SIMPLYP_P_EPC0_A] * c.A_catch;
     EPC0_NC = fl.nc_is_S ? EPC0_A : mp[SIMPLYP_P_EPC0_S] * c.A_catch;
@@ -506,7 +508,7 @@ SP_HD void end_day(const Hot& h, Cold& c, const Flags& fl, int dynamic_epc0, con
   const double QsS = xS * gate(xS * h.inv_fcd) * h.inv_TsS;
   const double xg = y[iVg] * h.inv_Tg - h.Qg_min;                // :668-670
   const double Qg = h.Qg_min + gate(xg * h.inv_Qgd) * xg;
-  y[iVg] = Qg / h.inv_Tg;
+  y[iVg] = Qg * c.T_g;                                           // :670
   const double VsNC = fl.post_nc_is_A ? y[iVsA] : y[iVsS];       // :676-681
   const double QsNC = fl.post_nc_is_A ? QsA : QsS;
   if (dynamic_epc0) {                                            // :684-703
@@ -516,8 +518,8 @@ SP_HD void end_day(const Hot& h, Cold& c, const Flags& fl, int dynamic_epc0, con
     c.PlabA = sp_max(c.PlabA, 0.0);
     c.TDPsNC = sp_max(c.TDPsNC, 0.0);
     c.PlabNC = sp_max(c.PlabNC, 0.0);
-    c.concA = c.TDPsA / y[iVsA];
-    c.concNC = c.TDPsNC / VsNC;
+    c.concA = c.TDPsA * sp_rcp(y[iVsA]);
+    c.concNC = c.TDPsNC * sp_rcp(VsNC);
   } else {                                                       // :707-715
     c.concA = aux.EPC0_A;
     c.concNC = aux.EPC0_NC;

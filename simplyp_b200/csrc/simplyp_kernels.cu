@@ -61,6 +61,7 @@ struct KArgs {
   const double* obs;            // cal: [V][D]
   const int* obs_desc;          // cal: [V][2]
   const double* obs_const;      // cal: [V][8]
+  const double* obs_log;        // cal: [V][D] natural log of the observations (NaN where there is none), or null
   double* stats;                // cal: [M][V][8]
   double* flux;                 // cal, S>1: [M][S][D][4]
   int* progress;                // S>1: [M][S] days completed (release/acquire flags of the routing wavefront)
@@ -296,10 +297,18 @@ struct RunIO : IOBase {
 
 // Calibration mode: nothing is written per day except (for S>1) the 4 fluxes the downstream reach
 // needs; observed days update the running sums of the fit statistics.
+// Running sums of the fit statistics of one (member, sub-catchment) item.  The quad kernel keeps them in SHARED
+// memory (STAT_SLOTS series per item: a reach has at most the six kinds Q, SS, TDP, PP, TP, SRP): the per-day
+// read-modify-write of eight sums per series in global memory was the largest stall of the day-boundary code.
+// Series beyond STAT_SLOTS on one reach, and the one-thread-per-item kernel, accumulate in stats[][][] directly.
+constexpr int STAT_SLOTS = 6;
+constexpr int STAT_STRIDE = STAT_SLOTS * 8 + 1;      // doubles per item; odd: the 8 quad leaders of a warp hit distinct banks
+
 struct CalIO : IOBase {
   double f_TDP;
-  __device__ CalIO(const KArgs& a_, int m_, int s_, ForcingRing* ring_, double f_TDP_)
-      : IOBase(a_, m_, s_, ring_), f_TDP(f_TDP_) {}
+  double* sacc;     // shared-memory accumulators of this item [STAT_SLOTS][8], or null
+  __device__ CalIO(const KArgs& a_, int m_, int s_, ForcingRing* ring_, double f_TDP_, double* sacc_ = nullptr)
+      : IOBase(a_, m_, s_, ring_), f_TDP(f_TDP_), sacc(sacc_) {}
 
   __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
     us[0] = us[1] = us[2] = us[3] = 0.0;
@@ -323,18 +332,21 @@ struct CalIO : IOBase {
       double* row = a.flux + (((size_t)m * a.S + s) * a.D + day) * 4;
       row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = acc[3];
     }
+    // simulated concentrations (model.py:784-793, :840-845): (flux/Qr)/A_catch
+    const double A = c.A_catch;
+    const double iq = sp_rcp(acc[0]) * sp_rcp(A);
+    const double tdp = acc[2] * iq, pp = acc[3] * iq;
+    int slot = 0;
     for (int v = 0; v < a.V; ++v) {
       if (__ldg(a.obs_desc + 2 * v) != s) continue;
+      const int k = slot++;
       const double o = __ldg(a.obs + (size_t)v * a.D + day);
       if (o != o) continue;  // no observation that day
       const int kind = __ldg(a.obs_desc + 2 * v + 1);
-      // simulated counterpart (model.py:784-793, :840-845)
-      const double A = c.A_catch;
-      const double tdp = (acc[2] / acc[0]) / A, pp = (acc[3] / acc[0]) / A;
       double sim;
       switch (kind) {
-        case SIMPLYP_V_Q:   sim = acc[0] * A * 1000.0 / 86400.0; break;
-        case SIMPLYP_V_SS:  sim = (acc[1] / acc[0]) / A; break;
+        case SIMPLYP_V_Q:   sim = acc[0] * A * (1000.0 / 86400.0); break;
+        case SIMPLYP_V_SS:  sim = acc[1] * iq; break;
         case SIMPLYP_V_TDP: sim = tdp; break;
         case SIMPLYP_V_PP:  sim = pp; break;
         case SIMPLYP_V_TP:  sim = tdp + pp; break;
@@ -344,29 +356,39 @@ struct CalIO : IOBase {
       const double* oc = a.obs_const + 8 * v;
       const double mo = __ldg(oc + OC_MEAN);
       const double em = __ldg(a.member_params + (size_t)m * SIMPLYP_NP_MEMBER + SIMPLYP_P_ERR_M0 + kind);
-      double* rs = a.stats + ((size_t)m * a.V + v) * SIMPLYP_NSTAT;
       const double d = o - sim;
-      const double dl = log(o) - log(sim);
       const double sg = em * sim;
+      // natural logs: of the observation precomputed once per run; of the simulated value by the branch-free
+      // sp_log, which needs a positive argument (anything else gives NaN, i.e. -inf log-likelihood, as np.log does)
+      const double lo = a.obs_log ? __ldg(a.obs_log + (size_t)v * a.D + day) : log(o);
+      const double ls = (sim > 0.0) ? sp_log(sim) : NAN;
+      const double lsg = (sg > 0.0) ? sp_log(sg) : NAN;
+      const double dl = lo - ls;
+      const double rsg = sp_rcp(sg);
       const double ds = sim - mo;
+      double* rs = (sacc != nullptr && k < STAT_SLOTS) ? sacc + 8 * k
+                                                       : a.stats + ((size_t)m * a.V + v) * SIMPLYP_NSTAT;
       rs[RS_N] += 1.0;
       rs[RS_SSE] += d * d;
       rs[RS_SSE_LOG] += dl * dl;
-      rs[RS_LL] += -0.91893853320467274178 - log(sg) - d * d / (2.0 * sg * sg);   // MCMC.ipynb:233-236
+      rs[RS_LL] += -0.91893853320467274178 - lsg - 0.5 * (d * rsg) * (d * rsg);   // MCMC.ipynb:233-236
       rs[RS_S1] += ds;
       rs[RS_S2] += ds * ds;
       rs[RS_SOS] += (o - mo) * ds;
       rs[RS_SABS] += fabs(d);
     }
   }
-  // turn the raw sums of this thread's series into the statistics of visualise_results.py:441-449
+  // turn the raw sums of this item's series into the statistics of visualise_results.py:441-449
   __device__ void finalise() const {
+    int slot = 0;
     for (int v = 0; v < a.V; ++v) {
       if (a.obs_desc[2 * v] != s) continue;
+      const int k = slot++;
       const double* oc = a.obs_const + 8 * v;
       double* rs = a.stats + ((size_t)m * a.V + v) * SIMPLYP_NSTAT;
-      const double n = rs[RS_N], sse = rs[RS_SSE], ssel = rs[RS_SSE_LOG], ll = rs[RS_LL];
-      const double s1 = rs[RS_S1], s2 = rs[RS_S2], sos = rs[RS_SOS], sabs = rs[RS_SABS];
+      const double* src = (sacc != nullptr && k < STAT_SLOTS) ? sacc + 8 * k : rs;
+      const double n = src[RS_N], sse = src[RS_SSE], ssel = src[RS_SSE_LOG], ll = src[RS_LL];
+      const double s1 = src[RS_S1], s2 = src[RS_S2], sos = src[RS_SOS], sabs = src[RS_SABS];
       const double ss_o = oc[OC_SS], ss_lo = oc[OC_SS_LOG], sum_o = oc[OC_SUM], std_o = oc[OC_STD];
       const double var_s = s2 - s1 * s1 / n;
       rs[SIMPLYP_ST_N] = n;
@@ -520,6 +542,14 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
   const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
 
+  // calibration: shared-memory accumulators of the fit statistics, behind the forcing ring
+  double* sacc = nullptr;
+  if (MODE == MODE_CAL) {
+    sacc = reinterpret_cast<double*>(ring + 1) + (size_t)(threadIdx.x >> 2) * STAT_STRIDE;
+    if ((threadIdx.x & 3) == 0)
+      for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = 0.0;
+    __syncwarp();
+  }
   QuadDev q;
   q.ql = threadIdx.x & 3;
   q.tab = s_exp2tab;
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     }
     return;
   } else if (MODE == MODE_CAL) {
-    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
+    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
     run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
     if (valid && q.ql == 0) io.finalise();
     cnt.status |= io.wait_status;
@@ -720,9 +750,10 @@ __global__ void cost_scatter_kernel(const unsigned* cost, unsigned* offsets, int
 
 // ------------------------------------------------------------------------------------------ obs constants
 // One block per observed series: n, mean, sum of squares about the mean (plain and log), sum, std.
-__global__ void obs_const_kernel(const double* obs, int D, double* obs_const) {
+__global__ void obs_const_kernel(const double* obs, int D, double* obs_const, double* obs_log) {
   const int v = blockIdx.x;
   const double* o = obs + (size_t)v * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) obs_log[(size_t)v * D + d] = log(o[d]);   // NaN stays NaN
   __shared__ double red[5][256];
   double n = 0, s = 0, sl = 0;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -804,7 +835,7 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
   size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_ticket,
-      off_progress, off_flux, off_obs_rank, off_sim_obs, total;
+      off_progress, off_flux, off_obs_log, off_obs_rank, off_sim_obs, total;
 };
 
 WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = false) {
@@ -824,6 +855,8 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
   L.off_flux = o;
   if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
+  L.off_obs_log = o;
+  if (cal) o = align_up(o + sizeof(double) * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1) * d.n_days);
   L.off_obs_rank = o;
   if (cal && ranks) o = align_up(o + sizeof(double) * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1) * d.n_days);
   L.off_sim_obs = o;
@@ -975,7 +1008,8 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const int block = 128;
     const int qpb = block / 4;
     const long long grid = (n_items_padded + qpb - 1) / qpb;
-    const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
+    const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
+                        (CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
     const int rc = order_members_by_cost(dims, opt, a, L, ws, st);
     if (rc) return rc;
     constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
@@ -1120,7 +1154,9 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
   if (V > 0) {
     SP_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * SIMPLYP_NSTAT * (size_t)dims->n_members * V, st));
     if (dims->n_days > 0) {
-      obs_const_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, reinterpret_cast<double*>(ws + L.off_oc));
+      obs_const_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, reinterpret_cast<double*>(ws + L.off_oc),
+                                          reinterpret_cast<double*>(ws + L.off_obs_log));
+      a.obs_log = reinterpret_cast<const double*>(ws + L.off_obs_log);
       g_launches.fetch_add(1);
       if (ranks) {
         obs_rank_kernel<<<V, 256, 0, st>>>(obs, dims->n_days, obs_rank, reinterpret_cast<double*>(ws + L.off_oc));

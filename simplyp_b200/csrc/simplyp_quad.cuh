@@ -566,7 +566,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       // Vr - L/(a_Q 86400) Qr^(1-b_Q) is conserved by ode_f (:127-131) and zero initially (:457-459): an error
       // along that direction is never damped and would random-walk over a 30-year record, so the volume carried
       // into the next day is put back on the curve (the reported Vr is the integrated one).
-      s.yB = q.pick(y[iMsus], y[iTDPr], y[iPPr], sp_exp((1.0 - h.bQ) * u_end) / h.cR);
+      s.yB = q.pick(y[iMsus], y[iTDPr], y[iPPr], sp_exp((1.0 - h.bQ) * u_end) * sp_rcp(h.cR));
       q.sync();
       if (q.leader()) {
         qm.c = c;
