@@ -153,7 +153,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -186,7 +186,8 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm),
+                       window="warm-up + timed steps")
         return out
 
 
@@ -236,13 +237,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from before the warm-up steps (nvidia-smi needs ~0.1 s to start and a timed region of 10
+    # steps lasts 0.15 s) to the end of the timed steps: every sample is taken under the bench load
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = _cabi.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
