@@ -126,6 +126,18 @@ SP_HD double sp_rcp(double x) {
 #endif
 }
 
+// 1/x to ~40 bits (one Newton step on the 20-bit hardware seed): for the reciprocal INSIDE the RHS evaluation, whose
+// accuracy requirement is the integration tolerance (1e-7), not the last bit.
+SP_HD double sp_rcp40(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Polynomial coefficients live in constant memory on the device: a DFMA can take a constant-bank operand
 // directly, whereas a 64-bit literal costs two extra move instructions every time it is rematerialised
 // (and with ~250 live registers the compiler rematerialises all of them inside the step loop).
@@ -178,10 +190,10 @@ SP_HD double sp_exp_core(double x) {
 
 // Table-driven e^x for the quad kernel: x = (64 m + j) ln2/64 + r with |r| <= ln2/128, e^x = 2^m * 2^(j/64) * e^r.
 // The reduction uses the 1.5*2^52 trick (the integer lands in the low word of the sum: no FRND/F2I), e^r is a
-// degree-5 polynomial (remainder r^6/6! < 4e-17) and 2^(j/64) comes from a 64-entry table (`tab`: shared memory on
+// degree-4 polynomial (remainder r^5/5! < 4e-14: far below the integration tolerance this function serves) and 2^(j/64) comes from a 64-entry table (`tab`: shared memory on
 // the device, kExp2Tab on the host).  The table entry is scaled by 2^m with integer arithmetic while the
 // polynomial is still being evaluated, so one multiply finishes the function.  |x| < 700, no range check.
-// Accuracy ~1.5 ulp.
+// Relative accuracy 4e-14.
 constexpr int EXP_TAB = 64;
 SP_CONST double kExpT[12] = {
     92.33248261689366,      // 64/ln2
@@ -216,9 +228,8 @@ SP_HD double sp_exp_tab_pre(double x, double t, const double* tab) {
   double r = fma(kf, kExpT[1], x);
   r = fma(kf, kExpT[2], r);
   const double r2 = r * r;
-  const double c = fma(r, kExpT[7], kExpT[6]);
   const double b = fma(r, kExpT[5], kExpT[4]);
-  const double p = fma(r2, fma(r2, c, b), 1.0 + r);
+  const double p = fma(r2, fma(r2, kExpT[6], b), 1.0 + r);      // 1 + r + r^2/2 + r^3/6 + r^4/24
   return p * sc;
 }
 SP_HD double sp_exp_tab(double x, const double* tab) { return sp_exp_tab_pre(x, fma(x, kExpT[0], kExpT[3]), tab); }
@@ -264,7 +275,7 @@ SP_HD double sp_clamp01(double u) {
 }
 SP_HD double gate(double u) {
   u = sp_clamp01(u);
-  return u * u * (3.0 - 2.0 * u);
+  return u * u * fma(-2.0, u, 3.0);
 }
 
 // ------------------------------------------------------------------------------------------

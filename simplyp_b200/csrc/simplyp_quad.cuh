@@ -75,11 +75,12 @@ SP_HD double qfma(double a, double b, double c) { return fma(a, b, c); }
 SP_HD double qgate(double u) { return gate(u); }
 SP_HD double qclamp01(double u) { return sp_clamp01(u); }
 SP_HD double qrcp(double x) { return sp_rcp(x); }
+SP_HD double qrcp40(double x) { return sp_rcp40(x); }
 SP_HD double qrcp_fast(double x) { return sp_rcp_fast(x); }
 SP_HD double qabs(double x) { return fabs(x); }
 SP_HD double qmax(double a, double b) { return sp_max(a, b); }
 #define SP_V4_MAP1(name, f) inline V4 name(const V4& a) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = f(a.v[l]); return r; }
-SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qclamp01, sp_clamp01) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
+SP_V4_MAP1(qgate, gate) SP_V4_MAP1(qclamp01, sp_clamp01) SP_V4_MAP1(qrcp, sp_rcp) SP_V4_MAP1(qrcp40, sp_rcp40) SP_V4_MAP1(qrcp_fast, sp_rcp_fast)
 SP_V4_MAP1(qabs, fabs)
 #undef SP_V4_MAP1
 inline V4 qmax(const V4& a, const V4& b) { V4 r; for (int l = 0; l < 4; ++l) r.v[l] = sp_max(a.v[l], b.v[l]); return r; }
@@ -191,7 +192,7 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   const T G = qfma(qgate(w) * w, c.g1, c.g0);
   const T u = q.bcast(yA, 3);
   const T Vr = q.bcast(yB, 3);
-  const T rV = qrcp(Vr);
+  const T rV = qrcp40(Vr);                  // 40 bits: the integration tolerance is 1e-7
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
   e = q.exp(qfma(c.eY, yA, c.eU * u));
   const T gsum = qfma(c.aSA, QsA, c.aSS * QsS) + c.aG * Qg;                  // ready before the exponential
