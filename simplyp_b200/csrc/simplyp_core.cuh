@@ -197,8 +197,8 @@ SP_HD double sp_exp_core(double x) {
 constexpr int EXP_TAB = 64;
 SP_CONST double kExpT[12] = {
     92.33248261689366,      // 64/ln2
-    -0.01083042468962958,    // -ln2/64, high part (22 trailing zero bits: k*hi is exact for |k| < 2^22)
-    -6.619564634077006e-12,  // -ln2/64, low part
+    -0.010830424696249145,   // -ln2/64 (nearest double)
+    0.0,                     // (unused)
     6755399441055744.0,      // 1.5*2^52
     0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 0.0, 0.0, 0.0, 0.0};
 // 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic)
@@ -225,12 +225,13 @@ SP_HD double sp_exp_tab_pre(double x, double t, const double* tab) {
   const int ki = (int)(unsigned)(sp_d2ll(t) & 0xffffffffLL);      // two's-complement integer in the low word
   // 2^(j/64) * 2^m: exponent field of the table entry plus m (off the critical path)
   const double sc = sp_ll2d(sp_d2ll(tab[ki & (EXP_TAB - 1)]) + ((long long)(ki >> 6) << 52));
-  double r = fma(kf, kExpT[1], x);
-  r = fma(kf, kExpT[2], r);
+  // one FMA reduces the argument: the product is exact inside the FMA, so the only error is |k| times the rounding
+  // of the constant ln2/64 (1.2e-18): 3e-15 for the largest arguments of the RHS (k_M ln Qr ~ 26), 8e-14 at |x| = 700
+  const double r = fma(kf, kExpT[1], x);
   const double r2 = r * r;
   const double b = fma(r, kExpT[5], kExpT[4]);
-  const double p = fma(r2, fma(r2, kExpT[6], b), 1.0 + r);      // 1 + r + r^2/2 + r^3/6 + r^4/24
-  return p * sc;
+  const double p = fma(r2, fma(r2, kExpT[6], b), r);              // e^r - 1 = r + r^2/2 + r^3/6 + r^4/24
+  return fma(sc, p, sc);
 }
 SP_HD double sp_exp_tab(double x, const double* tab) { return sp_exp_tab_pre(x, fma(x, kExpT[0], kExpT[3]), tab); }
 
