@@ -195,11 +195,11 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   const T rV = qrcp40(Vr);                  // 40 bits: the integration tolerance is 1e-7
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
   e = q.exp(qfma(c.eY, yA, c.eU * u));
-  const T gsum = qfma(c.aSA, QsA, c.aSS * QsS) + c.aG * Qg;                  // ready before the exponential
+  const T gsum = qfma(c.aG, Qg, qfma(c.aSA, QsA, qfma(c.aSS, QsS, c.a0)));   // ready before the exponential
   const T src0 = qfma(c.bSA, QsA, qfma(c.bSS, QsS, qfma(c.bG, Qg, c.b0)));
   const T mult = qfma(rV, c.mA, c.m0);
   const T qk = q.bcast(e, 2), Qr = q.bcast(e, 3);
-  const T L = (qfma(c.aE, e, c.a0) + gsum) + c.aR * Qr;
+  const T L = qfma(c.aR, Qr, qfma(c.aE, e, gsum));
   const T r = Qr * rV;                       // Qr/Vr
   const T out = yB * r;                      // outflow of the lane's in-stream mass (:145,147,166,168,178,180)
   dA = L * mult;                             // lane 3: du/dt = net/((1-b_Q) Vr)
