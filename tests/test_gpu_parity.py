@@ -416,3 +416,29 @@ def test_stiff_reach_vs_oracle(cabi, area):
     """The Rosenbrock path of the quad kernel (stiff main-stem-like reach) against LSODA/BDF at tight tolerance."""
     per_day = parity.check_stiff_chain(cabi.run_host, area, max_steps_per_day=100)
     assert per_day > 20
+
+
+def test_one_thread_per_item_kernel_still_agrees(cabi, golden_dir):
+    """The round-1 kernel (lanes_per_item = 1), kept for A/B measurements: same parity bound on Tarland 2004, and
+    its fused statistics agree with the quad kernel's to the integration tolerance."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+
+    def runner(forcing, member, sc, po, pid, opt):
+        opt.lanes_per_item = 1
+        return cabi.run_host(forcing, member, sc, po, pid, opt)
+
+    parity.check_tarland(runner, golden_dir, "y")
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    samples = ens.latin_hypercube(96, seed=12)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
+    forcing = pk.forcing_matrix(met)
+    st = {}
+    for lanes in (1, 4):
+        opt = spm.make_options(p_SU, p, dyn, topo, lanes_per_item=lanes)
+        st[lanes], dg = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+        assert not np.any(dg[..., 3])
+    for col in (1, 2, 4, 5, 6):      # NSE, log NSE, r2, bias, nRMSD
+        assert np.allclose(st[1][..., col], st[4][..., col], rtol=2e-4, atol=2e-5), col
+    assert np.array_equal(st[1][..., 0], st[4][..., 0])
