@@ -698,6 +698,10 @@ SP_HD double step_factor(double en) {
 // Device: fp32 lg2/ex2 with flush-to-zero and no range branches — an underflowing en^2 gives lg2 = -inf, hence
 // +inf, clamped to 5; an overflowing one gives 0, clamped to 0.2 (en^2 is never NaN here).
 // `expo` = -1/(2p) for an estimate of order p-1 ... i.e. -0.1 for the 5(4) pair, -0.125 for Kaps-Rentrop 4(3).
+#ifndef SP_CTRL_SAFETY
+#define SP_CTRL_SAFETY 0.9     // scripts/controller_exp.py: 0.95 saves 2.8 % attempts at the price of 1.5x the rejections
+#define SP_CTRL_MAXGROW 5.0
+#endif
 SP_HD double step_factor_sq(double en2, double expo = -0.1) {
 #if defined(__CUDA_ARCH__)
   float l, f;
@@ -705,12 +709,8 @@ SP_HD double step_factor_sq(double en2, double expo = -0.1) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
   l *= (float)expo;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(l));
-  return (double)fminf(fmaxf(0.9f * f, 0.2f), 5.0f);
+  return (double)fminf(fmaxf((float)SP_CTRL_SAFETY * f, 0.2f), (float)SP_CTRL_MAXGROW);
 #else
-#ifndef SP_CTRL_SAFETY
-#define SP_CTRL_SAFETY 0.9
-#define SP_CTRL_MAXGROW 5.0
-#endif
   if (!(en2 > 1e-38)) return SP_CTRL_MAXGROW;
   if (!(en2 < 1e38)) return 0.2;
   const double f = SP_CTRL_SAFETY * exp(expo * log(en2));
