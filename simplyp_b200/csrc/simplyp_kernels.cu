@@ -409,7 +409,6 @@ struct CalIO : IOBase {
 struct PilotIO : IOBase {
   using IOBase::IOBase;
   __device__ __forceinline__ void upstream(int, double (&us)[4]) const { us[0] = us[1] = us[2] = us[3] = 0.0; }
-  __device__ __forceinline__ bool wants_vr() const { return false; }
   __device__ __forceinline__ void emit(int, const double (&)[NL], double, const double (&)[NA], const double (&)[13],
                                        const Cold&) const {}
 };
