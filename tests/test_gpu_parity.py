@@ -442,3 +442,8 @@ def test_one_thread_per_item_kernel_still_agrees(cabi, golden_dir):
     for col in (1, 2, 4, 5, 6):      # NSE, log NSE, r2, bias, nRMSD
         assert np.allclose(st[1][..., col], st[4][..., col], rtol=2e-4, atol=2e-5), col
     assert np.array_equal(st[1][..., 0], st[4][..., 0])
+
+
+def test_against_the_reference_shipped_csvs(cabi, golden_dir):
+    """The CUDA path against the reference's own shipped golden CSVs (to the reference's solver noise)."""
+    parity.check_shipped_golden(cabi.run_host, golden_dir)

@@ -82,3 +82,8 @@ def test_stiff_reach_takes_the_rosenbrock_path(area):
     pair needs (one-thread-per-item program: 112 ... 690 per day)."""
     per_day = parity.check_stiff_chain(hostemu.run_quad, area, max_steps_per_day=100)
     assert per_day > 20
+
+
+@pytest.mark.parametrize("prog", ["quad", "scalar"])
+def test_against_the_reference_shipped_csvs(golden_dir, prog):
+    parity.check_shipped_golden(RUNNERS[prog], golden_dir)
