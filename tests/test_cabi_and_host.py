@@ -344,3 +344,17 @@ print("ok", dist.get_rank() if dist.is_initialized() else "")
         procs.append(subprocess.Popen([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_integration_md_stub_matches_the_header():
+    """The ctypes structures printed in INTEGRATION.md (the binding a maintainer would paste into the reference) have
+    the same fields, in the same order, as include/simplyp_b200.h and simplyp_b200/_cabi.py."""
+    from simplyp_b200 import _cabi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class Options(C.Structure):"):text.index("_dp, _ip, _lp")]
+    names = re.findall(r'\("([a-z_0-9]+)", C\.c_', block)
+    assert names == [f[0] for f in _cabi.SimplypOptions._fields_]
+    header = open(os.path.join(ROOT, "include", "simplyp_b200.h")).read()
+    body = header[header.index("typedef struct SimplypOptions {"):header.index("} SimplypOptions;")]
+    hnames = re.findall(r"^\s*(?:double|int32_t)\s+([a-z_0-9]+)", body, flags=re.M)
+    assert hnames == names
