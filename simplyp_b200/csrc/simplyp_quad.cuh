@@ -43,12 +43,15 @@
                               // (scripts/controller_exp.py)
 #endif
 #ifndef SP_STIFF_RATE
-#define SP_STIFF_RATE 300.0   // reach rate constant Qr/((1-b_Q) Vr) per day above which a day is integrated by the
-                              // Rosenbrock path (the explicit pair needs > ~100 attempts per day there)
+#define SP_STIFF_RATE 150.0   // reach rate constant Qr/((1-b_Q) Vr) per day above which a day is integrated by the
+                              // Rosenbrock path (the explicit pair needs more than ~50 attempts per day there, the
+                              // Rosenbrock path 45-55 whatever the rate); measured on configs 3/5: 300 -> 150 is
+                              // 14 % faster on config 5, equal on config 3
 #endif
 #ifndef SP_ROS_TOL_SCALE
-#define SP_ROS_TOL_SCALE 10.0 // Kaps-Rentrop's 3rd-order estimate is conservative: at 10x the tolerance its global error is
-                              // still below the explicit pair's (build/exp prototype: 1.2e-8 vs 3.6e-8 at rtol 1e-7)
+#define SP_ROS_TOL_SCALE 30.0 // Kaps-Rentrop's 3rd-order estimate is conservative: at 30x the tolerance the flows of a
+                              // stiff reach are still within 5e-7 of LSODA/BDF at 1e-10 and its end-of-day states
+                              // within 3e-6 (tests/...::test_stiff_reach_*), the explicit pair's own level
 #endif
 #ifndef SP_W_B
 #define SP_W_B 1.0     // weight of the slot-B (in-stream masses, Vr) terms of the error norm
