@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -843,8 +844,8 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   L.off_po = o;    o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
   L.off_pid = o;   o = align_up(o + sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
   L.off_order = o; o = align_up(o + sizeof(int) * (size_t)d.n_sc);
-  L.off_lvl_items = o; o = align_up(o + sizeof(long long) * ((size_t)d.n_sc + 1));   // at most n_sc levels
-  L.off_lvl_order = o; o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
+  L.off_lvl_items = o; o = align_up(o + sizeof(long long) * (2 * (size_t)d.n_sc + 1));   // <= 2 groups per level
+  L.off_lvl_order = o; o = align_up(o + sizeof(int) * (2 * (size_t)d.n_sc + 1));
   L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
   L.off_cost = o;  o = align_up(o + sizeof(unsigned) * (size_t)d.n_members);
   L.off_hist = o;  o = align_up(o + sizeof(unsigned) * COST_BUCKETS);
@@ -945,10 +946,35 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   if (nl < 0) return fail(SIMPLYP_EINVAL, "topology: parents must precede children in run order%s");
   const int E = po_host[S];
   const WsLayout L = ws_layout(dims, E, CAL);
+  // Items are laid out group by group; a group = one topological level, split (quad kernel) into the reaches that
+  // are expected to be stiff and the rest, so that the lock-step warps of a level hold either Rosenbrock items or
+  // explicit ones and do not execute both attempts per iteration.  The expectation is a host-side estimate from the
+  // first parameter set: reach rate constant at a nominal runoff of 3 mm/d over the whole upstream area
+  // (a_Q 86400/L (3 A_upstream/A_own)^b_Q / (1-b_Q), model.py:127-130) against the kernel's switching rate.  It
+  // only steers the grouping: the method itself is still chosen per item and day on the device.
+  std::vector<int> group(S, 0);
+  int n_groups = nl;
+  if (S > 1 && opt.lanes_per_item != 1) {
+    std::vector<double> scp((size_t)S * SIMPLYP_NP_SC), mp0(SIMPLYP_NP_MEMBER), area_up(S, 0.0);
+    SP_CUDA(cudaMemcpyAsync(scp.data(), a.sc_params, sizeof(double) * scp.size(), cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaMemcpyAsync(mp0.data(), a.member_params, sizeof(double) * mp0.size(), cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaStreamSynchronize(st));
+    const double aQ = mp0[SIMPLYP_P_A_Q], bQ = mp0[SIMPLYP_P_B_Q];
+    for (int s = 0; s < S; ++s) {
+      area_up[s] = scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+      for (int e = po_host[s]; e < po_host[s + 1]; ++e) area_up[s] += area_up[pid_host[e]];
+      const double qr = 3.0 * area_up[s] / scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+      const double rate = aQ * 86400.0 / scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_L_REACH] * pow(qr, bQ) / (1.0 - bQ);
+      group[s] = 2 * lvl[s] + ((rate > SP_STIFF_RATE) ? 0 : 1);
+    }
+    n_groups = 2 * nl;
+  } else {
+    for (int s = 0; s < S; ++s) group[s] = lvl[s];
+  }
   std::vector<int> order;
   order.reserve(S);
-  for (int l = 0; l < nl; ++l)
-    for (int s = 0; s < S; ++s) if (lvl[s] == l) order.push_back(s);
+  for (int g = 0; g < n_groups; ++g)
+    for (int s = 0; s < S; ++s) if (group[s] == g) order.push_back(s);
 
   if (S > 1 || E > 0) {
     if (!ws) return fail(SIMPLYP_EINVAL, "workspace required for n_sc > 1%s");
@@ -982,20 +1008,20 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   const long long n_items = (long long)S * dims.n_members;
   long long n_items_padded = ((long long)dims.n_members + 7) / 8 * 8;
   if (S > 1 && opt.lanes_per_item != 1) {
-    std::vector<long long> lvl_items(nl + 1, 0);
-    std::vector<int> lvl_order(nl + 1, 0);
-    for (int s = 0; s < S; ++s) lvl_order[lvl[s] + 1] += 1;
-    for (int l = 0; l < nl; ++l) {
-      const long long n_real = (long long)lvl_order[l + 1] * dims.n_members;
-      lvl_order[l + 1] += lvl_order[l];
-      lvl_items[l + 1] = lvl_items[l] + (n_real + 7) / 8 * 8;
+    std::vector<long long> lvl_items(n_groups + 1, 0);
+    std::vector<int> lvl_order(n_groups + 1, 0);
+    for (int s = 0; s < S; ++s) lvl_order[group[s] + 1] += 1;
+    for (int g = 0; g < n_groups; ++g) {
+      const long long n_real = (long long)lvl_order[g + 1] * dims.n_members;
+      lvl_order[g + 1] += lvl_order[g];
+      lvl_items[g + 1] = lvl_items[g] + (n_real + 7) / 8 * 8;       // an empty group takes no items
     }
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_items, lvl_items.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice, st));
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_order, lvl_order.data(), sizeof(int) * (nl + 1), cudaMemcpyHostToDevice, st));
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_items, lvl_items.data(), sizeof(long long) * (n_groups + 1), cudaMemcpyHostToDevice, st));
+    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_order, lvl_order.data(), sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, st));
     a.level_item_off = reinterpret_cast<const long long*>(ws + L.off_lvl_items);
     a.level_order_off = reinterpret_cast<const int*>(ws + L.off_lvl_order);
-    a.n_levels = nl;
-    n_items_padded = lvl_items[nl];
+    a.n_levels = n_groups;
+    n_items_padded = lvl_items[n_groups];
   }
   a.n_items_padded = n_items_padded;
   if (opt.lanes_per_item == 1) {
