@@ -235,6 +235,14 @@ int simplyp_sum_to_waterbody_device(const SimplypDims* dims, const double* out, 
                                     const double* member_params, const int32_t* reaches, int32_t n_reaches,
                                     double* waterbody, void* stream);
 
+/* daily_PET (inputs.py:232-312; Thornthwaite 1948 via :416-508) on the device, for a record of whole calendar
+ * years starting on 1 January: t_air[d * t_stride] daily mean air temperature, month_start[n_months + 1] = day index
+ * at which each calendar month starts (device), year_is_leap[n_months / 12] (device), latitude in degrees;
+ * pet[d * pet_stride] receives mm/day (stride 4 writes column 1 of a forcing matrix in place when pet = forcing + 1). */
+int simplyp_thornthwaite_pet_device(int32_t n_days, int32_t n_months, const double* t_air, int32_t t_stride,
+                                    const int32_t* month_start, const int32_t* year_is_leap, double latitude_deg,
+                                    double* pet, int32_t pet_stride, void* stream);
+
 /* Host-buffer forms: same arguments as HOST pointers; the library stages them through its own
  * (cached) device buffers on `device`, runs and copies the result back before returning. */
 int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* opt,

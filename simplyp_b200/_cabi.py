@@ -22,7 +22,7 @@ EXPORTS = [
     "simplyp_default_options", "simplyp_topology_levels", "simplyp_workspace_bytes",
     "simplyp_run_device", "simplyp_calibrate_device", "simplyp_run_host", "simplyp_calibrate_host",
     "simplyp_release_cache", "simplyp_launch_count", "simplyp_measure_fp64_peak",
-    "simplyp_measure_fp64_latency", "simplyp_sum_to_waterbody_device",
+    "simplyp_measure_fp64_latency", "simplyp_sum_to_waterbody_device", "simplyp_thornthwaite_pet_device",
 ]
 
 
@@ -86,6 +86,9 @@ def load():
     lib.simplyp_measure_fp64_latency.restype = C.c_double
     lib.simplyp_sum_to_waterbody_device.argtypes = [C.POINTER(SimplypDims), vp, vp, vp, vp, C.c_int32, vp, vp]
     lib.simplyp_sum_to_waterbody_device.restype = C.c_int
+    lib.simplyp_thornthwaite_pet_device.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, vp,
+                                                    C.c_int32, vp]
+    lib.simplyp_thornthwaite_pet_device.restype = C.c_int
     if lib.simplyp_abi_version() != 2:
         raise SimplypError("ABI version mismatch")
     _lib = lib
@@ -224,6 +227,15 @@ def sum_to_waterbody_device(dims, out_ptr, sc_ptr, member_ptr, reaches_ptr, n_re
     lib = require_device()
     _check(lib.simplyp_sum_to_waterbody_device(C.byref(dims), out_ptr, sc_ptr, member_ptr, reaches_ptr,
                                                int(n_reaches), wb_ptr, stream_ptr))
+
+
+def thornthwaite_pet_device(n_days, n_months, t_air_ptr, t_stride, month_start_ptr, year_is_leap_ptr, latitude_deg,
+                            pet_ptr, pet_stride, stream_ptr):
+    """Reference ``daily_PET`` (``inputs.py:232-312``) on device pointers; asynchronous on ``stream_ptr``."""
+    _check(load().simplyp_thornthwaite_pet_device(int(n_days), int(n_months), C.c_void_p(t_air_ptr), int(t_stride),
+                                                  C.c_void_p(month_start_ptr), C.c_void_p(year_is_leap_ptr),
+                                                  float(latitude_deg), C.c_void_p(pet_ptr), int(pet_stride),
+                                                  C.c_void_p(stream_ptr)))
 
 
 def workspace_bytes(dims, calibrate, rank_stats=False):

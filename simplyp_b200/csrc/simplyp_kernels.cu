@@ -719,6 +719,72 @@ __global__ void waterbody_kernel(const double* out, const double* sc_params, con
   w[10] = td * f_TDP;             // SRP_kg/day (:845)
 }
 
+// ------------------------------------------------------------------------------------------ Thornthwaite PET
+// daily_PET (inputs.py:232-312) for a record of whole calendar years, one block: monthly mean daylight hours from the
+// latitude (:416-445; FAO-56 eq. 24, 25, 34 at :370-414), monthly mean air temperature, Thornthwaite's monthly PET per
+// year (:447-508), divided by the days of the month, placed on the 16th and interpolated linearly to the days (the
+// days before the first and after the last 16th take that value, as pandas' limit_direction='both' does).
+// Dynamic shared memory: 2 * n_months doubles.
+__global__ void thornthwaite_kernel(int D, int NM, const double* t_air, int t_stride, const int* month_start,
+                                    const int* year_is_leap, double lat_rad, double* pet, int pet_stride) {
+  extern __shared__ double sh_pet[];
+  double* s_tmean = sh_pet;            // [NM] monthly mean air temperature, negative values counted as zero
+  double* s_pet = sh_pet + NM;         // [NM] PET per day of the month (value on the 16th)
+  __shared__ double s_dlh[2][12];
+  const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  if (threadIdx.x < 24) {
+    const int leap = threadIdx.x / 12, mon = threadIdx.x % 12;
+    int doy = 1;
+    for (int k = 0; k < mon; ++k) doy += mdays[k] + ((leap && k == 1) ? 1 : 0);
+    const int n = mdays[mon] + ((leap && mon == 1) ? 1 : 0);
+    double total = 0.0;
+    for (int k = 0; k < n; ++k, ++doy) {
+      const double sd = 0.409 * sin((2.0 * M_PI / 365.0) * doy - 1.39);
+      const double c = -tan(lat_rad) * tan(sd);
+      total += (24.0 / M_PI) * acos(fmin(fmax(c, -1.0), 1.0));
+    }
+    s_dlh[leap][mon] = total / n;
+  }
+  for (int m = threadIdx.x; m < NM; m += blockDim.x) {
+    const int d0 = month_start[m], d1 = month_start[m + 1];
+    double sum = 0.0;
+    for (int d = d0; d < d1; ++d) sum += t_air[(size_t)d * t_stride];
+    const double t = sum / (d1 - d0);
+    s_tmean[m] = t >= 0.0 ? t : 0.0;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < NM; m += blockDim.x) {
+    const int y = m / 12, mon = m % 12, leap = year_is_leap[y] != 0;
+    double heat = 0.0;
+    for (int k = 0; k < 12; ++k) {
+      const double x = s_tmean[12 * y + k] / 5.0;
+      if (x > 0.0) heat += pow(x, 1.514);
+    }
+    const double a = (6.75e-07 * pow(heat, 3.0)) - (7.71e-05 * pow(heat, 2.0)) + (1.792e-02 * heat) + 0.49239;
+    const double N = mdays[mon] + ((leap && mon == 1) ? 1 : 0);
+    const double ta = s_tmean[m];
+    s_pet[m] = (1.6 * (s_dlh[leap][mon] / 12.0) * (N / 30.0) * pow(10.0 * ta / heat, a) * 10.0) / N;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    int lo = 0, hi = NM;                            // month with month_start[lo] <= d < month_start[lo+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (month_start[mid] <= d) lo = mid; else hi = mid;
+    }
+    const int m0 = (d >= month_start[lo] + 15) ? lo : lo - 1, m1 = m0 + 1;
+    double v;
+    if (m0 < 0) v = s_pet[0];
+    else if (m1 >= NM) v = s_pet[NM - 1];
+    else {
+      const int x0 = month_start[m0] + 15, x1 = month_start[m1] + 15;
+      const double slope = (s_pet[m1] - s_pet[m0]) / (double)(x1 - x0);
+      v = slope * (double)(d - x0) + s_pet[m0];
+    }
+    pet[(size_t)d * pet_stride] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ cost ordering
 // Counting sort of the members by pilot cost, heaviest first: hist[] -> start offsets (one block), then scatter.
 __global__ void cost_scan_kernel(unsigned* hist) {
@@ -1296,6 +1362,22 @@ int simplyp_sum_to_waterbody_device(const SimplypDims* dims, const double* out, 
   waterbody_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       out, sc_params, member_params, reaches, n_reaches, dims->n_members, dims->n_sc, dims->n_days,
       dims->n_sc_param_sets, waterbody);
+  g_launches.fetch_add(1);
+  SP_CUDA(cudaGetLastError());
+  return SIMPLYP_OK;
+}
+
+int simplyp_thornthwaite_pet_device(int32_t n_days, int32_t n_months, const double* t_air, int32_t t_stride,
+                                    const int32_t* month_start, const int32_t* year_is_leap, double latitude_deg,
+                                    double* pet, int32_t pet_stride, void* stream) {
+  if (!t_air || !month_start || !year_is_leap || !pet) return fail(SIMPLYP_EINVAL, "null argument%s");
+  if (n_days <= 0 || n_months <= 0 || n_months % 12 != 0 || t_stride <= 0 || pet_stride <= 0)
+    return fail(SIMPLYP_EINVAL, "PET needs whole calendar years (n_months a multiple of 12)%s");
+  if (n_months > 2880) return fail(SIMPLYP_EINVAL, "PET: more than 240 years%s");
+  if (!(latitude_deg >= -90.0 && latitude_deg <= 90.0)) return fail(SIMPLYP_EINVAL, "latitude outside -90..90 degrees%s");
+  if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  thornthwaite_kernel<<<1, 256, sizeof(double) * 2 * (size_t)n_months, static_cast<cudaStream_t>(stream)>>>(
+      n_days, n_months, t_air, t_stride, month_start, year_is_leap, latitude_deg * (M_PI / 180.0), pet, pet_stride);
   g_launches.fetch_add(1);
   SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;

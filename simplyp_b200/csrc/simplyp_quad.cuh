@@ -550,6 +550,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     }
 
     // ---- end of the day: post-ODE algebra (:643-724), output --------------------------------------
+#ifdef SP_DAY_HOOK
+    SP_DAY_HOOK(io, day, n_steps);                // analysis builds only (scripts/): per-day attempt counts
+#endif
     {
       double y[NL], yraw[NL], acc[NA], non[13];
       const double u_end = q.first(q.bcast(s.yA, 3));

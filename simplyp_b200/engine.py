@@ -133,3 +133,23 @@ class Engine:
             _cabi.sum_to_waterbody_device(dims, out.data_ptr(), sc_params.data_ptr(), member_params.data_ptr(),
                                           r.data_ptr(), int(r.numel()), wb.data_ptr(), stream)
         return wb
+
+    # ------------------------------------------------------------------ Thornthwaite PET
+    def thornthwaite_pet(self, t_air, month_start, year_is_leap, latitude_deg, out=None, out_stride=1):
+        """Reference ``daily_PET`` (``inputs.py:232-312``) on the device: ``t_air`` [D] (device or host),
+        ``month_start`` [n_months + 1] day index at which each calendar month of the record starts,
+        ``year_is_leap`` [n_months / 12]; returns PET [D] in mm/day (or writes ``out`` with ``out_stride``,
+        e.g. column 1 of a forcing matrix: ``out=forcing[:, 1], out_stride=4``); asynchronous."""
+        torch = _torch()
+        t = self.to_device(t_air, np.float64)
+        ms = torch.as_tensor(np.asarray(month_start, dtype=np.int32), device=self.device)
+        lp = torch.as_tensor(np.asarray(year_is_leap, dtype=np.int32), device=self.device)
+        D, NM = int(t.numel()), int(ms.numel()) - 1
+        if out is None:
+            out = torch.empty(D, dtype=torch.float64, device=self.device)
+            out_stride = 1
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.thornthwaite_pet_device(D, NM, t.data_ptr(), 1, ms.data_ptr(), lp.data_ptr(), latitude_deg,
+                                          out.data_ptr(), out_stride, stream)
+        return out

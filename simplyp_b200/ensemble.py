@@ -154,3 +154,124 @@ def calibrate_ensemble(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, ob
         stats = all_gather_stats(stats, M)
     torch.cuda.synchronize(eng.device)
     return stats, labels, diag
+
+
+# --------------------------------------------------------------------------- full-output ensemble container
+def _safe_name(col):
+    return col.replace("/", "_per_")
+
+
+def run_ensemble_to_dir(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, samples, out_dir, columns=None,
+                        members_per_chunk=None, step_len=1.0, rtol=None, atol=None, engine=None):
+    """Full daily output of an ensemble written as one ``.npy`` per raw variable.
+
+    The members are integrated in chunks; while the GPU integrates chunk k+1 (compute stream), chunk k travels to
+    PINNED host memory on a copy stream and is scattered by the host into memory-mapped ``<variable>.npy`` files of
+    shape ``[M][S][D]`` (float64) — the reference's raw columns (``model.py:737-745``), ``/`` in a name written as
+    ``_per_``.  ``manifest.json`` lists variables, shapes, member parameters (``samples.npz``), sub-catchment ids,
+    dates and the integrator diagnostics (``diag.npy`` [M][S][4]).  Two device buffers and two pinned buffers of
+    ``members_per_chunk * S * D * 200`` bytes each are used (default: about 1 GiB per buffer).
+
+    Returns the manifest dict.  Ranks of a ``torch.distributed`` job each write their member shard
+    (``shard_bounds``) into files of the full shape opened in ``r+`` mode, rank 0 creating them first.
+    """
+    import json
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from .engine import Engine
+    from .model import make_options
+
+    p_LU, p_SC = p_LU.copy(deep=True), p_SC.copy(deep=True)
+    pk.validate_land_use(p_SC, p["SC_list"])
+    pk.check_erosion_windows(p)
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = make_options(p_SU, p, dynamic_options, topo, step_len, rtol, atol)
+    member, sc = pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    M, S, D = member.shape[0], len(topo.sc_ids), len(met_df)
+    cols = list(pk.RAW_COLS) if columns is None else list(columns)
+    col_idx = [pk.RAW_COLS.index(c) for c in cols]
+    rank, world = (dist.get_rank(), dist.get_world_size()) if (dist.is_available() and dist.is_initialized()) else (0, 1)
+    lo, hi = shard_bounds(M, world, rank)
+
+    os.makedirs(out_dir, exist_ok=True)
+    paths = {c: os.path.join(out_dir, _safe_name(c) + ".npy") for c in cols}
+    diag_path = os.path.join(out_dir, "diag.npy")
+    if rank == 0:
+        for c in cols:
+            np.lib.format.open_memmap(paths[c], mode="w+", dtype=np.float64, shape=(M, S, D)).flush()
+        np.lib.format.open_memmap(diag_path, mode="w+", dtype=np.int64, shape=(M, S, pk.NDIAG)).flush()
+        np.savez(os.path.join(out_dir, "samples.npz"), **{k.replace(":", "__"): np.asarray(v) for k, v in samples.items()})
+    if world > 1:
+        dist.barrier()
+    files = {c: np.load(paths[c], mmap_mode="r+") for c in cols}
+    diag_file = np.load(diag_path, mmap_mode="r+")
+
+    eng = engine or Engine()
+    row_bytes = S * D * pk.NOUT * 8
+    if members_per_chunk is None:
+        members_per_chunk = max(1, (1 << 30) // max(row_bytes, 1))
+    chunk = int(max(1, min(members_per_chunk, hi - lo))) if hi > lo else 1
+    d_forc = eng.to_device(pk.forcing_matrix(met_df))
+    d_mem = eng.to_device(member[lo:hi]) if hi > lo else None
+    d_sc = eng.to_device(sc if sc.shape[0] == 1 else sc[lo:hi]) if hi > lo else None
+    dev_buf = [torch.empty((chunk, S, D, pk.NOUT), dtype=torch.float64, device=eng.device) for _ in range(2)]
+    dev_diag = [torch.zeros((chunk, S, pk.NDIAG), dtype=torch.int64, device=eng.device) for _ in range(2)]
+    pin_buf = [torch.empty((chunk, S, D, pk.NOUT), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    pin_diag = [torch.empty((chunk, S, pk.NDIAG), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=eng.device)
+    computed = [torch.cuda.Event() for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    pending = []                                      # (buffer, first member, count) in flight to the host
+
+    def drain(item):
+        b, m0, n = item
+        copied[b].synchronize()
+        host = pin_buf[b].numpy()
+        for c, j in zip(cols, col_idx):
+            files[c][m0:m0 + n] = host[:n, :, :, j]
+        diag_file[m0:m0 + n] = pin_diag[b].numpy()[:n]
+
+    with torch.cuda.device(eng.device):
+        compute_stream = torch.cuda.current_stream()
+        k = 0
+        for m0 in range(lo, hi, chunk):
+            n = min(chunk, hi - m0)
+            b = k % 2
+            if len(pending) == 2:                     # buffer b is still travelling / being scattered
+                drain(pending.pop(0))
+            scp = d_sc if d_sc.shape[0] == 1 else d_sc[m0 - lo:m0 - lo + n]
+            eng.run(d_forc, d_mem[m0 - lo:m0 - lo + n], scp, topo.parent_offsets, topo.parent_ids, opt,
+                    out=dev_buf[b][:n], diag=dev_diag[b][:n])
+            computed[b].record(compute_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(computed[b])
+                pin_buf[b][:n].copy_(dev_buf[b][:n], non_blocking=True)
+                pin_diag[b][:n].copy_(dev_diag[b][:n], non_blocking=True)
+                copied[b].record(copy_stream)
+            pending.append((b, m0, n))
+            k += 1
+        while pending:
+            drain(pending.pop(0))
+    for f in files.values():
+        f.flush()
+    diag_file.flush()
+    if world > 1:
+        dist.barrier()
+    manifest = {
+        "format": "simplyp_b200 ensemble container v1",
+        "variables": {c: os.path.basename(paths[c]) for c in cols},
+        "shape": [M, S, D], "dtype": "float64", "axes": ["member", "sub_catchment", "day"],
+        "sub_catchments": [int(s) for s in topo.sc_ids],
+        "dates": [str(met_df.index[0].date()), str(met_df.index[-1].date())],
+        "diag": "diag.npy", "samples": "samples.npz",
+        "options": {"rtol": float(opt.rtol), "atol": float(opt.atol),
+                    "dynamic_epc0": int(opt.dynamic_epc0), "dynamic_erodibility": int(opt.dynamic_erodibility)},
+        "members_per_chunk": chunk, "world_size": world,
+    }
+    if rank == 0:
+        with open(os.path.join(out_dir, "manifest.json"), "w") as f:
+            json.dump(manifest, f, indent=1)
+    return manifest

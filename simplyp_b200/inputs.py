@@ -320,3 +320,28 @@ def daily_PET(latitude, met_df):
     met_df = met_df.join(pet_df)
     met_df["PET"] = met_df["PET"].interpolate(method="linear", limit=32, limit_direction="both")
     return met_df
+
+
+def daily_PET_device(latitude, met_df, engine=None):
+    """:func:`daily_PET` with the arithmetic on the GPU (``thornthwaite_kernel`` behind the C-ABI entry point
+    ``simplyp_thornthwaite_pet_device``): same arguments, same returned frame, same ``ValueError`` for a record
+    that is not made of whole calendar years (reference ``inputs.py:232-312``).  No CPU fallback."""
+    from .engine import Engine
+
+    if not -90.0 <= latitude <= 90.0:
+        check_latitude_rad(deg2rad(latitude))
+    idx = met_df.index
+    years = sorted(set(idx.year))
+    counts = met_df["T_air"].groupby([idx.year, idx.month]).size()
+    for year in years:
+        if len(counts.loc[year]) < 12:
+            raise ValueError("PET calc requires input met data for whole calendar years."
+                             "Year {0!r} does not contain 12 months. Check input met data,"
+                             "or change the start/end dates in the parameter file".format(year))
+    month_start = np.concatenate([[0], np.cumsum(counts.to_numpy())]).astype(np.int32)
+    leap = np.array([1 if calendar.isleap(y) else 0 for y in years], dtype=np.int32)
+    eng = engine or Engine()
+    pet = eng.thornthwaite_pet(met_df["T_air"].to_numpy(dtype=np.float64, copy=True), month_start, leap, float(latitude))
+    out = met_df.drop(columns=["PET"]) if "PET" in met_df.columns else met_df.copy()
+    out["PET"] = pet.cpu().numpy()
+    return out

@@ -447,3 +447,75 @@ def test_one_thread_per_item_kernel_still_agrees(cabi, golden_dir):
 def test_against_the_reference_shipped_csvs(cabi, golden_dir):
     """The CUDA path against the reference's own shipped golden CSVs (to the reference's solver noise)."""
     parity.check_shipped_golden(cabi.run_host, golden_dir)
+
+
+@pytest.mark.gpu
+def test_thornthwaite_pet_on_device(cabi, golden_dir):
+    """SURVEY §8f rank 3 (PET half): daily_PET (inputs.py:232-312) as a device kernel.  Against the host function
+    (whose helpers are pinned bit-identical to the reference's, test_oracle_pins) over the 30-year Tarland record,
+    and against the reference helpers' monthly values on the 16th of each month; tolerance 1e-12 relative (CUDA's
+    pow/sin/tan/acos differ from libm's in the last bits).  Error behaviour equals the host function's."""
+    import calendar
+    import json
+    import pandas as pd
+    import simplyp_b200 as sp
+    from simplyp_b200 import inputs
+    z = np.load(os.path.join(golden_dir, "tarland_met.npz"), allow_pickle=True)
+    idx = pd.date_range("1981-01-01", periods=len(z["T_air"]), freq="D")
+    met = pd.DataFrame({"T_air": z["T_air"].astype(float), "PET": z["PET"].astype(float)}, index=idx)
+    want = sp.daily_PET(57.1, met)
+    got = inputs.daily_PET_device(57.1, met)
+    assert list(got.columns) == list(want.columns) and got.index.equals(want.index)
+    assert np.allclose(got["PET"].to_numpy(), want["PET"].to_numpy(), rtol=1e-12, atol=0)
+    assert "PET" in met.columns and np.array_equal(met["PET"].to_numpy(), z["PET"].astype(float))   # input untouched
+    with open(os.path.join(golden_dir, "ref_pet.json")) as f:
+        ref = json.load(f)
+    for year, rec in ref["years"].items():
+        for mon in range(12):
+            n = calendar.monthrange(int(year), mon + 1)[1]
+            assert got.loc["%s-%02d-16" % (year, mon + 1), "PET"] == pytest.approx(rec["pet_mm_month"][mon] / n, rel=1e-12)
+    # a southern latitude and a record with months below zero (counted as zero, inputs.py:489)
+    cold = pd.DataFrame({"T_air": z["T_air"].astype(float) - 4.0}, index=idx)
+    a, b = inputs.daily_PET_device(-33.9, cold["1981":"1989"]), sp.daily_PET(-33.9, cold["1981":"1989"])
+    assert np.allclose(a["PET"].to_numpy(), b["PET"].to_numpy(), rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        inputs.daily_PET_device(57.1, met.iloc[:400])
+    with pytest.raises(ValueError):
+        inputs.daily_PET_device(95.0, met)
+
+
+def test_ensemble_container_equals_one_shot_run(cabi, tmp_path):
+    """the full-output ensemble container (chunked runs, pinned asynchronous D2H, one .npy per
+    raw variable) holds bit-for-bit what a single full-output launch of all members returns, for a chunk size that
+    does not divide the ensemble (ragged last chunk) and for a column subset."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from simplyp_b200.engine import Engine
+    from tests.golden.networks import network5_inputs
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    p, p_LU, p_SC, p_struc = network5_inputs(p, p_LU, p_SC, p_struc)
+    met = met.iloc[:90]
+    samples = ens.latin_hypercube(7, seed=11)
+    man = ens.run_ensemble_to_dir(met, p_struc, p_SU, p_LU, p_SC, p, dyn, samples, str(tmp_path / "all"),
+                                  members_per_chunk=3)
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    p_SC2 = p_SC.copy(deep=True)
+    pk.validate_land_use(p_SC2, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC2, topo.sc_ids), samples)
+    eng = Engine(0)
+    out, diag = eng.run(eng.to_device(pk.forcing_matrix(met)), eng.to_device(member), eng.to_device(sc),
+                        topo.parent_offsets, topo.parent_ids, opt)
+    out, diag = out.cpu().numpy(), diag.cpu().numpy()
+    assert man["shape"] == [7, 5, 90] and len(man["variables"]) == pk.NOUT
+    for j, col in enumerate(pk.RAW_COLS):
+        got = np.load(os.path.join(str(tmp_path / "all"), man["variables"][col]))
+        assert got.shape == (7, 5, 90) and np.array_equal(got, out[:, :, :, j]), col
+    d = np.load(os.path.join(str(tmp_path / "all"), "diag.npy"))
+    assert np.array_equal(d[:, :, 3], diag[:, :, 3]) and (d[:, :, 0] > 0).all()
+    with open(os.path.join(str(tmp_path / "all"), "manifest.json")) as f:
+        assert json.load(f)["sub_catchments"] == [int(s) for s in topo.sc_ids]
+    man2 = ens.run_ensemble_to_dir(met, p_struc, p_SU, p_LU, p_SC, p, dyn, samples, str(tmp_path / "two"),
+                                   columns=["Qr", "TDP_kg/day"], members_per_chunk=100)
+    assert sorted(man2["variables"]) == ["Qr", "TDP_kg/day"]
+    got = np.load(os.path.join(str(tmp_path / "two"), "TDP_kg_per_day.npy"))
+    assert np.array_equal(got, out[:, :, :, pk.RAW_COLS.index("TDP_kg/day")])

@@ -119,3 +119,19 @@ def test_snow_restatement_matches_shipped_golden(golden_dir):
     assert np.allclose(D_end, tc["D_snow"].to_numpy(), rtol=0, atol=1e-12)
     assert np.allclose(0.02 * P, tc["Qq"].to_numpy(), rtol=1e-13, atol=0)
     assert abs(P.sum() - 953.26) < 0.01 and abs(D_end.max() - 42.74) < 1e-9
+
+
+def test_thornthwaite_helpers_equal_the_reference(golden_dir):
+    """Host Thornthwaite helpers (simplyp_b200/inputs.py) against values produced by the UNMODIFIED reference helpers
+    (inputs.py:315-508; fixture by tests/golden/make_pet_golden.py): bit-identical."""
+    import calendar
+    import json
+    from simplyp_b200 import inputs
+    with open(os.path.join(golden_dir, "ref_pet.json")) as f:
+        ref = json.load(f)
+    lat = inputs.deg2rad(ref["latitude_deg"])
+    assert inputs.monthly_mean_daylight_hours(lat, 1983) == ref["dlh_normal"]
+    assert inputs.monthly_mean_daylight_hours(lat, 1984) == ref["dlh_leap"]
+    for year, rec in ref["years"].items():
+        dlh = ref["dlh_leap"] if calendar.isleap(int(year)) else ref["dlh_normal"]
+        assert inputs.annual_thornthwaite(rec["monthly_t"], dlh, year=int(year)) == rec["pet_mm_month"], year
