@@ -79,8 +79,30 @@ struct KArgs {
   const int* perm;              // [M] member handled by item idx, or null
   unsigned* cost;               // pilot: [M] step attempts
   unsigned* hist;               // pilot: [COST_BUCKETS] histogram of the costs
+  int* plan;                    // placement of a cost-ordered ensemble on the SMs (see PlanShape), or null
+  int plan_nsm, plan_ny, plan_np, plan_q;
 };
 constexpr int COST_BUCKETS = 4096;
+
+// Placement of a cost-ordered, latency-bound ensemble (2 resident blocks per SM, B virtual blocks of 32 members).
+// The launch has exactly as many blocks as there are lists; a block does not take the virtual block blockIdx.x but
+// claims a LIST by where it lands: the first block to arrive on an SM (%smid) takes the next first-list, the second
+// one the second-list that belongs to it.  With Q = max(0, B - 2 nSM) virtual blocks too many for the machine:
+//   first-list t < nY = nSM - Q : heavy virtual block t;              its second-list: virtual block nY + t (t < nP)
+//   first-list nY + x, x < Q    : light blocks xb+Q+x then B-1-x;     its second-list: light block xb+x
+// where xb = nY + nP and cost_scatter_kernel has laid the members out so that virtual blocks [0, nY) are the heaviest
+// in descending order, [nY, nY+nP) their partners in ASCENDING order (the heaviest block shares its SM with the
+// lightest partner) and [xb, B) the 3Q lightest blocks in descending order (the two blocks that share a slot are
+// taken from the lightest 2Q, a heavier one with a lighter one; the block beside them from the Q above).  So the hardware never queues a block (a queued block starts
+// only when the first resident one ends, 7.6 ms into a 14 ms run at 10^4 members), and the two light blocks that must
+// share a slot run next to a third light block that leaves them the SM early.  Every list is claimed exactly once
+// whatever the placement: a block that cannot have its list takes the last one still free.
+constexpr int PLAN_MAX_SM = 1024;                  // %smid is folded into this range
+constexpr int PLAN_FIRST_NEXT = 0;
+constexpr int PLAN_SM_ARR = 16;                    // [PLAN_MAX_SM] blocks that have arrived on the SM
+constexpr int PLAN_SM_LIST = PLAN_SM_ARR + PLAN_MAX_SM;         // [PLAN_MAX_SM] 1 + first-list of the SM, -1: none
+constexpr int PLAN_CLAIMED = PLAN_SM_LIST + PLAN_MAX_SM;        // [2 * PLAN_MAX_SM] list taken?
+constexpr int PLAN_INTS = PLAN_CLAIMED + 2 * PLAN_MAX_SM;       // zeroed before every launch
 
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
 enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
@@ -110,6 +132,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_test_parity(unsigned long long* bar, unsigned parity) {
   unsigned ok;
@@ -484,21 +509,75 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
 // instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
 enum { MODE_RUN = 0, MODE_CAL = 1, MODE_PILOT = 2 };
+// First virtual block of a list of the placement plan (-1: the list does not exist); lists [0, nSM) are the
+// first-lists, list nSM + t is the second-list of first-list t.
+__device__ __forceinline__ int plan_list_head(const KArgs& a, int list) {
+  const int nY = a.plan_ny, nP = a.plan_np, Q = a.plan_q, xb = nY + nP;
+  if (list < a.plan_nsm) return list < nY ? list : xb + Q + (list - nY);
+  const int t = list - a.plan_nsm;
+  if (t < nY) return t < nP ? nY + t : -1;
+  return t < a.plan_nsm ? xb + (t - nY) : -1;
+}
+// virtual block that follows `vb` in its list, or -1
+__device__ __forceinline__ int plan_list_next(const KArgs& a, int vb) {
+  const int Q = a.plan_q, x = vb - (a.plan_ny + a.plan_np + Q);
+  return (x >= 0 && x < Q) ? a.plan_ny + a.plan_np + 3 * Q - 1 - x : -1;
+}
+// Thread 0 of a block claims a list (see the PLAN_* comment) and returns its first virtual block.
+__device__ int plan_claim(const KArgs& a) {
+  int* plan = a.plan;
+  const int nSM = a.plan_nsm;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  smid &= (PLAN_MAX_SM - 1);
+  const int slot = atomicAdd(plan + PLAN_SM_ARR + smid, 1);
+  int* claimed = plan + PLAN_CLAIMED;
+  int list = -1;
+  if (slot == 0) {
+    const int t = atomicAdd(plan + PLAN_FIRST_NEXT, 1);
+    if (t < nSM && atomicCAS(claimed + t, 0, 1) == 0) list = t;
+    __threadfence();
+    atomicExch(plan + PLAN_SM_LIST + smid, list >= 0 ? list + 1 : -1);
+  } else if (slot == 1) {
+    int v = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(plan + PLAN_SM_LIST + smid) : "memory");
+    } while (v == 0 && clock64() - t0 < (1ll << 20));
+    if (v > 0 && plan_list_head(a, nSM + v - 1) >= 0 && atomicCAS(claimed + nSM + v - 1, 0, 1) == 0) list = nSM + v - 1;
+  }
+  for (int l = 2 * nSM - 1; list < 0 && l >= 0; --l)
+    if (plan_list_head(a, l) >= 0 && atomicCAS(claimed + l, 0, 1) == 0) list = l;
+  return list < 0 ? -1 : plan_list_head(a, list);
+}
+
 template <int MODE, int MINB, bool STIFF>
 __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
-  __shared__ unsigned s_vblock;
+  __shared__ int s_vblock;
   __shared__ double s_exp2tab[EXP_TAB];
+  // the placement plan exists for the 2-blocks-per-SM build of an ensemble of one sub-catchment only
+  constexpr bool PLAN = (MINB == 2) && !STIFF && (MODE != MODE_PILOT);
   if (threadIdx.x < EXP_TAB) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
-  unsigned vblock = blockIdx.x;
-  if (a.ticket != nullptr) {
-    if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
+  int vblock = (int)blockIdx.x;
+#ifdef SP_TIMELINE
+  unsigned long long sp_timeline_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sp_timeline_t0));
+#endif
+  if (PLAN && a.plan != nullptr) {
+    if (threadIdx.x == 0) s_vblock = plan_claim(a);
+    __syncthreads();
+    vblock = s_vblock;
+    if (vblock < 0) return;
+  } else if (a.ticket != nullptr) {
+    if (threadIdx.x == 0) s_vblock = (int)atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
     __syncthreads();
     vblock = s_vblock;
   }
   const int quads_per_block = blockDim.x >> 2;
   QuadMem* qmem = reinterpret_cast<QuadMem*>(smem_cold);
   ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)quads_per_block * (sizeof(QuadMem) / sizeof(double)));
+  for (;;) {                                       // one pass per virtual block of a claimed list (else one pass)
   if (threadIdx.x == 0) {
     ring->n_consumers = blockDim.x >> 5;          // the warps of the block
     for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
@@ -580,6 +659,29 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
     dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
     dg[SIMPLYP_DG_STATUS] = cnt.status;
+#ifdef SP_TIMELINE                                  // analysis builds (scripts/exp_timeline.py): when and where the warp ran
+    unsigned long long t1; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dg[SIMPLYP_DG_REJECTED] = (long long)sp_timeline_t0;
+    dg[SIMPLYP_DG_RHS] = (long long)t1;
+    dg[SIMPLYP_DG_STATUS] = (long long)smid | ((long long)vblock << 16) | ((long long)(threadIdx.x >> 5) << 40) |
+                            ((long long)cnt.rejected << 44);      // cnt.rejected holds the warp's lock-step attempts here
+#endif
+  }
+  if (!(PLAN && a.plan != nullptr)) break;
+  // next virtual block of the list: every warp has left the forcing ring and the shared-memory state of its quads
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FORC_SLOTS; ++i) mbar_inval(&ring->full[i]);
+    s_vblock = plan_list_next(a, vblock);
+  }
+  __syncthreads();
+  vblock = s_vblock;
+  if (vblock < 0) break;
+#ifdef SP_TIMELINE
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sp_timeline_t0));
+#endif
   }
 }
 
@@ -806,11 +908,25 @@ __global__ void cost_scan_kernel(unsigned* hist) {
 #pragma unroll
   for (int k = 0; k < PER; ++k) { hist[COST_BUCKETS - 1 - (PER * threadIdx.x + k)] = run; run += loc[k]; }
 }
-__global__ void cost_scatter_kernel(const unsigned* cost, unsigned* offsets, int* perm, int M) {
+// Member layout of a planned launch (PLAN_* comment).  r = rank of the member, heaviest first.
+//  * the `solo` heaviest members each lead a warp of their own whose other seven quads hold light members (the
+//    lightest of the partner region), so that the longest lock-step chain of the launch is one member's step count,
+//    not the per-day maximum over eight similar heavy members;
+//  * the blocks of the partner region [nY, nY + n_rev) are stored in reverse order (lightest first).
+struct MemberLayout { int solo, nY, n_rev, fill_end; };
+__global__ void cost_scatter_kernel(const unsigned* cost, unsigned* offsets, int* perm, int M, MemberLayout L) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const unsigned c = cost[m];
-  const unsigned pos = atomicAdd(&offsets[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+  int pos = (int)atomicAdd(&offsets[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);   // rank, heaviest first
+  const int K = L.solo, fill_begin = L.fill_end - 7 * K;
+  if (pos < K) pos = 8 * pos;
+  else if (pos >= fill_begin && pos < L.fill_end) { const int t = pos - fill_begin; pos = 8 * (t / 7) + 1 + t % 7; }
+  else {
+    if (pos < fill_begin) pos += 7 * K;
+    const int blk = pos >> 5;
+    if (blk >= L.nY && blk < L.nY + L.n_rev) pos = ((L.nY + (L.n_rev - 1 - (blk - L.nY))) << 5) | (pos & 31);
+  }
   perm[pos] = m;
 }
 
@@ -900,7 +1016,7 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_ticket,
+  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_plan, off_ticket,
       off_progress, off_flux, off_obs_log, off_obs_rank, off_sim_obs, total;
 };
 
@@ -916,6 +1032,7 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   L.off_cost = o;  o = align_up(o + sizeof(unsigned) * (size_t)d.n_members);
   L.off_hist = o;  o = align_up(o + sizeof(unsigned) * COST_BUCKETS);
   L.off_perm = o;  o = align_up(o + sizeof(int) * (size_t)d.n_members);
+  L.off_plan = o;  if (d.n_sc == 1) o = align_up(o + sizeof(int) * (size_t)PLAN_INTS);
   L.off_ticket = o; o = align_up(o + sizeof(int));
   L.off_progress = o;
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
@@ -996,7 +1113,31 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE_PILOT, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
   else simplyp_quad_kernel<MODE_PILOT, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
-  cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members);
+  // latency-bound regime (2 blocks per SM, at most a quarter wave too many): planned placement, see PLAN_*
+  MemberLayout lay = {0, 0, 0, 0};
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const char* e_plan = getenv("SIMPLYP_SM_PLAN");
+  if (quad_minblocks(grid) == 2 && n_sm > 0 && n_sm <= PLAN_MAX_SM && grid > n_sm && dims.n_members >= 2048 &&
+      !(e_plan && atoi(e_plan) == 0)) {
+    const int B = (int)grid, Q = B > 2 * n_sm ? B - 2 * n_sm : 0;
+    const int nY = n_sm - Q, nP = (B - nY - 3 * Q) < nY ? (B - nY - 3 * Q) : nY;
+    if (nY > 0 && nP > 0 && 3 * Q <= B - nY) {
+      int solo = dims.n_members / 400 / 4 * 4;       // one block in about twelve of the heavy blocks
+      if (const char* e = getenv("SIMPLYP_SOLO_WARPS")) { const int v = atoi(e); if (v >= 0) solo = v; }
+      if (8 * solo > 32 * nY || 7 * solo > 16 * nP) solo = 0;
+      lay.solo = solo;
+      lay.nY = nY;
+      lay.n_rev = nP - ((Q == 0 && dims.n_members % 32 != 0) ? 1 : 0);   // a ragged last block stays last
+      const long long pe = 32ll * (nY + nP);
+      lay.fill_end = (int)(pe < dims.n_members ? pe : dims.n_members);
+      int* plan = reinterpret_cast<int*>(ws + L.off_plan);
+      SP_CUDA(cudaMemsetAsync(plan, 0, sizeof(int) * PLAN_INTS, st));
+      a.plan = plan;
+      a.plan_nsm = n_sm; a.plan_ny = nY; a.plan_np = nP; a.plan_q = Q;
+    }
+  }
+  cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members, lay);
   g_launches.fetch_add(3);
   SP_CUDA(cudaGetLastError());
   a.perm = perm;
@@ -1107,7 +1248,11 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of
     // the 2-blocks-per-SM variant
     if (S > 1) simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
-    else if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2, false><<<(unsigned)grid, block, smem, st>>>(a);
+    else if (quad_minblocks(grid) == 2) {
+      // planned placement: one block per list (n_sm first-lists, n_p + q second-lists), all resident at once
+      const unsigned g = a.plan ? (unsigned)(a.plan_nsm + a.plan_np + a.plan_q) : (unsigned)grid;
+      simplyp_quad_kernel<MODE, 2, false><<<g, block, smem, st>>>(a);
+    }
     else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);
     else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(a);
   }

@@ -453,6 +453,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     q.sync();
   }
   unsigned n_steps = 0, n_rej = 0, n_rhs = 0;
+#ifdef SP_TIMELINE
+  unsigned sp_lockstep_iters = 0;
+#endif
   int status = 0;
   double snow_depth = mp[SIMPLYP_P_D_SNOW_0];       // only used with snow_on_device
   const double T1 = opt.step_len;
@@ -489,6 +492,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
 
     // ---- step loop: lock-step over the quads of a warp ------------------------------------------
     while (q.any(active)) {
+#ifdef SP_TIMELINE
+      ++sp_lockstep_iters;                        // analysis builds: attempts the WARP executed (lock-step)
+#endif
       const double rem = T1 - t;
       const bool last = hstep * 1.0000001 >= rem;
       const double hh = active ? (last ? rem : hstep) : hstep;
@@ -587,6 +593,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   }
   cnt.steps = n_steps;
   cnt.rejected = n_rej;
+#ifdef SP_TIMELINE
+  cnt.rejected = sp_lockstep_iters;
+#endif
   cnt.rhs_evals = n_rhs;
   cnt.status = status;
   (void)Kf;

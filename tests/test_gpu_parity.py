@@ -519,3 +519,31 @@ def test_ensemble_container_equals_one_shot_run(cabi, tmp_path):
     assert sorted(man2["variables"]) == ["Qr", "TDP_kg/day"]
     got = np.load(os.path.join(str(tmp_path / "two"), "TDP_kg_per_day.npy"))
     assert np.array_equal(got, out[:, :, :, pk.RAW_COLS.index("TDP_kg/day")])
+
+
+@pytest.mark.parametrize("M", [4800, 6001, 9500, 10000])
+def test_planned_placement_is_invisible_in_the_results(cabi, M, monkeypatch):
+    """Latency-bound ensembles (more blocks than SMs, at most a quarter wave beyond 2 blocks per SM) are placed on the
+    SMs by plan (claim by %smid, reversed partner blocks, warps led by one heavy member, chained light blocks): the
+    statistics and diagnostics of every member must be bit-identical to the plain launch.  Sizes: a few partner
+    blocks only (4800), a ragged last block (6001), one and seventeen blocks beyond the resident set (9500, 10000)."""
+    import torch
+    import bench
+    from simplyp_b200 import model as spm, packing as pk
+    from simplyp_b200.engine import Engine
+    eng = Engine(0)
+    w = bench.build_workload("2004", M)
+    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, None, None)
+    forcing = w["forcing"][:100]
+    obs_m = np.ascontiguousarray(w["obs_m"][:, :100])
+    args = (eng.to_device(forcing), eng.to_device(w["member"]), eng.to_device(w["sc"]), w["topo"].parent_offsets,
+            w["topo"].parent_ids, eng.to_device(obs_m), eng.to_device(w["desc"]), opt)
+    res = {}
+    for plan in ("0", "1"):
+        monkeypatch.setenv("SIMPLYP_SM_PLAN", plan)
+        stats, diag = eng.calibrate(*args)
+        torch.cuda.synchronize()
+        res[plan] = (stats.cpu().numpy(), diag.cpu().numpy())
+    assert np.array_equal(res["0"][0], res["1"][0], equal_nan=True)
+    assert np.array_equal(res["0"][1], res["1"][1])
+    assert (res["1"][1][:, 0, 0] > 0).all() and (res["1"][1][:, 0, 3] == 0).all()      # every member ran, status clean
