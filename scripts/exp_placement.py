@@ -13,6 +13,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 cfgs = sys.argv[2:] or ["0:0", "1:0", "1:24", "1:d", "1:48", "0:0", "1:d"]
 w = bench.build_workload("2004", M)
 opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, None, None)
+opt.pilot_days = int(os.environ.get("PILOT_DAYS", "0"))
 d_forc = eng.to_device(w["forcing"]); d_mem = eng.to_device(w["member"][:M]); d_sc = eng.to_device(w["sc"][:M])
 d_obs = eng.to_device(w["obs_m"]); d_desc = eng.to_device(w["desc"])
 V = w["obs_m"].shape[0]
