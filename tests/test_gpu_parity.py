@@ -547,3 +547,13 @@ def test_planned_placement_is_invisible_in_the_results(cabi, M, monkeypatch):
     assert np.array_equal(res["0"][0], res["1"][0], equal_nan=True)
     assert np.array_equal(res["0"][1], res["1"][1])
     assert (res["1"][1][:, 0, 0] > 0).all() and (res["1"][1][:, 0, 3] == 0).all()      # every member ran, status clean
+    if M == 6001:                                  # the full-output mode takes the same placement
+        runs = {}
+        for plan in ("0", "1"):
+            monkeypatch.setenv("SIMPLYP_SM_PLAN", plan)
+            out, diag = eng.run(args[0][:70], args[1], args[2], args[3], args[4], opt)
+            torch.cuda.synchronize()
+            runs[plan] = (out.cpu().numpy(), diag.cpu().numpy())
+            del out
+        assert np.array_equal(runs["0"][0], runs["1"][0]) and np.array_equal(runs["0"][1], runs["1"][1])
+        assert np.isfinite(runs["1"][0]).all()
