@@ -127,8 +127,14 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "Tarland forcing/obs fixtures; "
         "Latin-hypercube parameter sets (seed 20260101)",
-        "config": {"workload": "Tarland %s, LHS ensemble, 1 sub-catchment, Dynamic_EPC0/erodibility on" % args.period,
-                   "members_per_step": per_core * cores, "days": days_per_member, "rtol": 0.01, "atol": "odeint default"},
+        "config": {"workload": "Tarland %s (D=%d days, S=1), %d-member LHS ensemble per GPU, fused NSE/log-NSE/"
+                               "log-likelihood vs observed Q and TDP, Dynamic_EPC0/erodibility on"
+                               % (args.period, days_per_member, args.members),
+                   "sample": "each step integrates a %d-member Latin-hypercube sample drawn by the same generator and seed "
+                             "(bounded sample; member-SC-days/s does not depend on the ensemble size on the CPU)"
+                             % (per_core * cores),
+                   "members_per_step": per_core * cores, "days": days_per_member, "sub_catchments": 1,
+                   "rtol": 0.01, "atol": "odeint default (the reference's own solver settings, model.py:640)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d members x %d days per step, one member per task on %d processes, "
                                    "scipy odeint (LSODA) rtol=0.01 as the reference calls it" % (per_core * cores, days_per_member, cores)},
