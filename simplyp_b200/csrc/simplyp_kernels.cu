@@ -79,7 +79,15 @@ struct KArgs {
   const int* perm;              // [M] member handled by item idx, or null
   unsigned* cost;               // pilot: [M] step attempts
   unsigned* hist;               // pilot: [COST_BUCKETS] histogram of the costs
-  int* plan;                    // placement of a cost-ordered ensemble on the SMs (see PlanShape), or null
+  // The pilot is the FIRST PART of the run: the same kernel integrates days [0, pilot days) in member order, stores
+  // every member's midnight state (carry) and its step attempts (cost); the main launch continues at day_begin.
+  QuadCarry* carry;             // [M] or null
+  double* carry_stats;          // cal: [M][STAT_SLOTS * 8] shared-memory fit-statistic sums at the hand-over, or null
+  int day_begin;                // first day this launch integrates (main launch after a pilot), else 0
+  int day_end;                  // one past the last day this launch integrates (D, or the pilot's days); D stays the
+                                // length of the record, i.e. the stride of forcing / obs / out
+  int pilot_pass;               // 1: this launch is the pilot (writes cost / hist / carry, no diagnostics, no finalise)
+  int* plan;                    // placement of a cost-ordered ensemble on the SMs (PLAN_* below), or null
   int plan_nsm, plan_ny, plan_np, plan_q;
 };
 constexpr int COST_BUCKETS = 4096;
@@ -431,14 +439,6 @@ struct CalIO : IOBase {
   }
 };
 
-// Pilot run: integrates, writes nothing per day.
-struct PilotIO : IOBase {
-  using IOBase::IOBase;
-  __device__ __forceinline__ void upstream(int, double (&us)[4]) const { us[0] = us[1] = us[2] = us[3] = 0.0; }
-  __device__ __forceinline__ void emit(int, const double (&)[NL], double, const double (&)[NA], const double (&)[13],
-                                       const Cold&) const {}
-};
-
 // ------------------------------------------------------------------------------------------ K1
 template <bool CAL>
 __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a) {
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // MINB = resident blocks per SM the register allocation is made for: 4 (128 registers, 16 warps per SM) when the
 // ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
 // instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
-enum { MODE_RUN = 0, MODE_CAL = 1, MODE_PILOT = 2 };
+enum { MODE_RUN = 0, MODE_CAL = 1 };
 // First virtual block of a list of the placement plan (-1: the list does not exist); lists [0, nSM) are the
 // first-lists, list nSM + t is the second-list of first-list t.
 __device__ __forceinline__ int plan_list_head(const KArgs& a, int list) {
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   __shared__ int s_vblock;
   __shared__ double s_exp2tab[EXP_TAB];
   // the placement plan exists for the 2-blocks-per-SM build of an ensemble of one sub-catchment only
-  constexpr bool PLAN = (MINB == 2) && !STIFF && (MODE != MODE_PILOT);
+  constexpr bool PLAN = (MINB == 2) && !STIFF;
   if (threadIdx.x < EXP_TAB) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
   int vblock = (int)blockIdx.x;
 #ifdef SP_TIMELINE
@@ -622,11 +622,16 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
 
   // calibration: shared-memory accumulators of the fit statistics, behind the forcing ring
+  const bool resume = a.carry != nullptr && !a.pilot_pass;
+  const QuadCarry* cin = resume ? a.carry + m : nullptr;
+  QuadCarry* cout = a.pilot_pass ? a.carry + m : nullptr;
   double* sacc = nullptr;
   if (MODE == MODE_CAL) {
     sacc = reinterpret_cast<double*>(ring + 1) + (size_t)(threadIdx.x >> 2) * STAT_STRIDE;
-    if ((threadIdx.x & 3) == 0)
-      for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = 0.0;
+    if ((threadIdx.x & 3) == 0) {
+      const double* src = resume ? a.carry_stats + (size_t)m * (STAT_SLOTS * 8) : nullptr;
+      for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = src ? src[i] : 0.0;
+    }
     __syncwarp();
   }
   QuadDev q;
@@ -634,24 +639,30 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   q.tab = s_exp2tab;
   QuadMem& qm = qmem[threadIdx.x >> 2];
   ThreadCounters cnt;
-  if (MODE == MODE_PILOT) {
-    PilotIO io(a, m, s, ring);
-    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
+  if (MODE == MODE_CAL) {
+    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
+    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+    if (valid && q.ql == 0) {
+      if (a.pilot_pass) {
+        double* dst = a.carry_stats + (size_t)m * (STAT_SLOTS * 8);
+        for (int i = 0; i < STAT_SLOTS * 8; ++i) dst[i] = sacc[i];
+      } else {
+        io.finalise();
+      }
+    }
+    cnt.status |= io.wait_status;
+  } else {
+    RunIO io(a, m, s, ring);
+    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+    cnt.status |= io.wait_status;
+  }
+  if (a.pilot_pass) {                                // the pilot's product: the cost of every member
     if (valid && q.ql == 0) {
       const unsigned c = (unsigned)cnt.steps;
       a.cost[m] = c;
       atomicAdd(&a.hist[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
     }
     return;
-  } else if (MODE == MODE_CAL) {
-    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
-    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
-    if (valid && q.ql == 0) io.finalise();
-    cnt.status |= io.wait_status;
-  } else {
-    RunIO io(a, m, s, ring);
-    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.D, valid, qm, io, cnt);
-    cnt.status |= io.wait_status;
   }
   if (a.diag && valid && q.ql == 0) {
     long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
@@ -1016,7 +1027,7 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_plan, off_ticket,
+  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket,
       off_progress, off_flux, off_obs_log, off_obs_rank, off_sim_obs, total;
 };
 
@@ -1033,6 +1044,10 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   L.off_hist = o;  o = align_up(o + sizeof(unsigned) * COST_BUCKETS);
   L.off_perm = o;  o = align_up(o + sizeof(int) * (size_t)d.n_members);
   L.off_plan = o;  if (d.n_sc == 1) o = align_up(o + sizeof(int) * (size_t)PLAN_INTS);
+  L.off_carry = o;
+  if (d.n_sc == 1 && d.n_members >= 512) o = align_up(o + sizeof(QuadCarry) * (size_t)d.n_members);
+  L.off_carry_stats = o;
+  if (d.n_sc == 1 && d.n_members >= 512 && cal) o = align_up(o + sizeof(double) * STAT_SLOTS * 8 * (size_t)d.n_members);
   L.off_ticket = o; o = align_up(o + sizeof(int));
   L.off_progress = o;
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
@@ -1094,24 +1109,32 @@ int quad_minblocks(long long grid) {
 }
 
 // Pilot + counting sort: fills a.perm (one sub-catchment, quad kernel).  3 small launches + the pilot.
+template <int MODE>
 int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KArgs& a, const WsLayout& L, char* ws,
                           cudaStream_t st) {
   const int days = opt.pilot_days > 0 ? opt.pilot_days : 8;
   if (opt.pilot_days < 0 || !ws || dims.n_sc != 1 || dims.n_members < 512 || dims.n_days < 8 * days) return SIMPLYP_OK;
+  // the pilot is the run's own first `days` days (same kernel, member order): it leaves every member's midnight
+  // state in the carry area, and the main launch continues from there in cost order
+  a.carry = reinterpret_cast<QuadCarry*>(ws + L.off_carry);
+  a.carry_stats = reinterpret_cast<double*>(ws + L.off_carry_stats);
   KArgs p = a;
-  p.D = days;
+  p.day_end = days;
   p.diag = nullptr;
   p.perm = nullptr;
+  p.pilot_pass = 1;
   p.cost = reinterpret_cast<unsigned*>(ws + L.off_cost);
   p.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
+  a.day_begin = days;
   int* perm = reinterpret_cast<int*>(ws + L.off_perm);
   SP_CUDA(cudaMemsetAsync(p.hist, 0, sizeof(unsigned) * COST_BUCKETS, st));
   const int block = 128, qpb = block / 4;
   const long long grid = ((long long)dims.n_members + qpb - 1) / qpb;
-  const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing);
-  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE_PILOT, 2, false><<<(unsigned)grid, block, smem, st>>>(p);
-  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE_PILOT, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
-  else simplyp_quad_kernel<MODE_PILOT, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
+  const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
+                      (MODE == MODE_CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
+  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2, false><<<(unsigned)grid, block, smem, st>>>(p);
+  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
+  else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
   // latency-bound regime (2 blocks per SM, at most a quarter wave too many): planned placement, see PLAN_*
   MemberLayout lay = {0, 0, 0, 0};
@@ -1242,9 +1265,9 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const long long grid = (n_items_padded + qpb - 1) / qpb;
     const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
                         (CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
-    const int rc = order_members_by_cost(dims, opt, a, L, ws, st);
-    if (rc) return rc;
     constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
+    const int rc = order_members_by_cost<MODE>(dims, opt, a, L, ws, st);
+    if (rc) return rc;
     // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of
     // the 2-blocks-per-SM variant
     if (S > 1) simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
@@ -1266,6 +1289,7 @@ KArgs base_args(const SimplypDims& dims, const SimplypOptions& opt, const double
   KArgs a;
   memset(&a, 0, sizeof(a));
   a.M = dims.n_members; a.S = dims.n_sc; a.D = dims.n_days; a.Msc = dims.n_sc_param_sets;
+  a.day_end = dims.n_days;
   a.V = dims.n_obs_series;
   a.topt = make_topt(opt);
   a.sc_qr0 = opt.sc_qr0;

@@ -423,6 +423,16 @@ struct QuadMem {
 };
 static_assert(sizeof(QuadMem) == 57 * sizeof(double), "QuadMem: odd double stride keeps 64-bit quad accesses conflict-free");
 
+// State of one item between two launches that integrate consecutive parts of its record (the cost pilot integrates
+// the first days in member order; the main launch continues from there in cost order instead of repeating them).
+struct QuadCarry {
+  QuadMem qm;
+  double yA[4], yB[4];        // slots A and B of the four lanes at midnight
+  double hstep, snow_depth;
+  unsigned n_steps, n_rej, n_rhs;
+  int status;
+};
+
 // IO policy concept of the quad program (all calls are made by every lane of the quad unless stated):
 //   void wait(int day);                          // block until forcing and upstream inputs of `day` exist
 //   void forcing(int day, double& P, double& E, double& doy, double& T_air);
@@ -437,7 +447,8 @@ static_assert(sizeof(QuadMem) == 57 * sizeof(double), "QuadMem: odd double strid
 // sub-catchment, where the reach rate constant stays below ~150 per day and the extra code would only cost registers).
 template <bool STIFF, class Q, class IO>
 SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0, int nc_last,
-                    const ThreadOptions& opt, int n_days, bool valid, QuadMem& qm, IO& io, ThreadCounters& cnt) {
+                    const ThreadOptions& opt, int n_days, bool valid, QuadMem& qm, IO& io, ThreadCounters& cnt,
+                    int day_begin = 0, const QuadCarry* carry_in = nullptr, QuadCarry* carry_out = nullptr) {
   using T = typename Q::T;
   QuadCoef<Q> qc;
   QuadState<Q> s;
@@ -460,8 +471,17 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   double snow_depth = mp[SIMPLYP_P_D_SNOW_0];       // only used with snow_on_device
   const double T1 = opt.step_len;
   double hstep = 0.05 * T1;
+  if (carry_in != nullptr) {                        // continue a record: everything that crosses midnight
+    s.yA = q.pick(carry_in->yA[0], carry_in->yA[1], carry_in->yA[2], carry_in->yA[3]);
+    s.yB = q.pick(carry_in->yB[0], carry_in->yB[1], carry_in->yB[2], carry_in->yB[3]);
+    hstep = carry_in->hstep;
+    snow_depth = carry_in->snow_depth;
+    n_steps = carry_in->n_steps; n_rej = carry_in->n_rej; n_rhs = carry_in->n_rhs; status = carry_in->status;
+    if (q.leader()) qm = carry_in->qm;
+    q.sync();
+  }
 
-  for (int day = 0; day < n_days; ++day) {
+  for (int day = day_begin; day < n_days; ++day) {
     // ---- start of the day: pre-ODE algebra (:497-618) -----------------------------------------
     io.wait(day);
     {
@@ -589,6 +609,20 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
         }
       }
       q.sync();
+    }
+  }
+  if (carry_out != nullptr) {
+    const double a0 = q.first(q.bcast(s.yA, 0)), a1 = q.first(q.bcast(s.yA, 1)), a2 = q.first(q.bcast(s.yA, 2)),
+                 a3 = q.first(q.bcast(s.yA, 3));
+    const double b0 = q.first(q.bcast(s.yB, 0)), b1 = q.first(q.bcast(s.yB, 1)), b2 = q.first(q.bcast(s.yB, 2)),
+                 b3 = q.first(q.bcast(s.yB, 3));
+    if (q.leader() && valid) {
+      carry_out->qm = qm;
+      carry_out->yA[0] = a0; carry_out->yA[1] = a1; carry_out->yA[2] = a2; carry_out->yA[3] = a3;
+      carry_out->yB[0] = b0; carry_out->yB[1] = b1; carry_out->yB[2] = b2; carry_out->yB[3] = b3;
+      carry_out->hstep = hstep;
+      carry_out->snow_depth = snow_depth;
+      carry_out->n_steps = n_steps; carry_out->n_rej = n_rej; carry_out->n_rhs = n_rhs; carry_out->status = status;
     }
   }
   cnt.steps = n_steps;

@@ -539,21 +539,30 @@ def test_planned_placement_is_invisible_in_the_results(cabi, M, monkeypatch):
     args = (eng.to_device(forcing), eng.to_device(w["member"]), eng.to_device(w["sc"]), w["topo"].parent_offsets,
             w["topo"].parent_ids, eng.to_device(obs_m), eng.to_device(w["desc"]), opt)
     res = {}
-    for plan in ("0", "1"):
-        monkeypatch.setenv("SIMPLYP_SM_PLAN", plan)
+    for plan in ("0", "1", "no pilot"):
+        monkeypatch.setenv("SIMPLYP_SM_PLAN", "0" if plan == "0" else "1")
+        opt.pilot_days = -1 if plan == "no pilot" else 0
         stats, diag = eng.calibrate(*args)
         torch.cuda.synchronize()
         res[plan] = (stats.cpu().numpy(), diag.cpu().numpy())
+    opt.pilot_days = 0
     assert np.array_equal(res["0"][0], res["1"][0], equal_nan=True)
     assert np.array_equal(res["0"][1], res["1"][1])
+    # the pilot is the first 8 days of the run itself (the main launch continues from its midnight state in another
+    # member order): a run without pilot, integrated in one piece, must give the same bits
+    assert np.array_equal(res["no pilot"][0], res["1"][0], equal_nan=True)
+    assert np.array_equal(res["no pilot"][1], res["1"][1])
     assert (res["1"][1][:, 0, 0] > 0).all() and (res["1"][1][:, 0, 3] == 0).all()      # every member ran, status clean
     if M == 6001:                                  # the full-output mode takes the same placement
         runs = {}
-        for plan in ("0", "1"):
-            monkeypatch.setenv("SIMPLYP_SM_PLAN", plan)
+        for plan in ("0", "1", "no pilot"):
+            monkeypatch.setenv("SIMPLYP_SM_PLAN", "0" if plan == "0" else "1")
+            opt.pilot_days = -1 if plan == "no pilot" else 0
             out, diag = eng.run(args[0][:70], args[1], args[2], args[3], args[4], opt)
             torch.cuda.synchronize()
             runs[plan] = (out.cpu().numpy(), diag.cpu().numpy())
             del out
+        opt.pilot_days = 0
         assert np.array_equal(runs["0"][0], runs["1"][0]) and np.array_equal(runs["0"][1], runs["1"][1])
+        assert np.array_equal(runs["no pilot"][0], runs["1"][0]) and np.array_equal(runs["no pilot"][1], runs["1"][1])
         assert np.isfinite(runs["1"][0]).all()
