@@ -1132,8 +1132,17 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   const long long grid = ((long long)dims.n_members + qpb - 1) / qpb;
   const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
                       (MODE == MODE_CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
-  if (quad_minblocks(grid) == 2) simplyp_quad_kernel<MODE, 2, false><<<(unsigned)grid, block, smem, st>>>(p);
-  else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
+  // register variant of the pilot pass (the variants give the same bits): when the 2-blocks-per-SM build would leave
+  // a few blocks queued behind the resident ones, the 3-blocks build runs them all at once
+  int pilot_minb = quad_minblocks(grid);
+  {
+    int dev0 = 0, nsm0 = 0;
+    if (cudaGetDevice(&dev0) == cudaSuccess) cudaDeviceGetAttribute(&nsm0, cudaDevAttrMultiProcessorCount, dev0);
+    if (pilot_minb == 2 && nsm0 > 0 && grid > 2ll * nsm0) pilot_minb = 3;
+    if (const char* e = getenv("SIMPLYP_PILOT_MINBLOCKS")) { const int v = atoi(e); if (v >= 2 && v <= 4) pilot_minb = v; }
+  }
+  if (pilot_minb == 2) simplyp_quad_kernel<MODE, 2, false><<<(unsigned)grid, block, smem, st>>>(p);
+  else if (pilot_minb == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
   else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
   // latency-bound regime (2 blocks per SM, at most a quarter wave too many): planned placement, see PLAN_*
