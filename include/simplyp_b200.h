@@ -179,8 +179,10 @@ typedef struct SimplypOptions {
   int32_t threads_per_block; /* 0 = library default (scalar kernel only) */
   int32_t lanes_per_item;    /* lanes that integrate one (member, sub-catchment): 0 = default (4, the quad
                                 kernel), 4, or 1 (one thread per item, the round-1 kernel kept for A/B runs) */
-  int32_t pilot_days;        /* ensembles of one sub-catchment: days of the pilot run whose step counts order the
-                                members over the lock-step warps (0 = default 8, < 0 = no pilot) */
+  int32_t pilot_days;        /* ensembles of one sub-catchment: the first `pilot_days` days are integrated in member
+                                order by a pilot launch whose step counts order the members over the lock-step warps;
+                                the main launch continues from its midnight state (0 = default 8, < 0 = no pilot;
+                                the results do not depend on it) */
   int32_t rank_stats;        /* calibration: also reduce Spearman's r (stores the simulated value of every observed
                                 day, M*V*D*8 bytes of workspace, and ranks them on the device afterwards) */
   int32_t snow_on_device;    /* 1: snow_hydrol_inputs (inputs.py:159-210) runs per member on the device (see forcing) */
