@@ -20,6 +20,7 @@
 
 #include "simplyp_thread.cuh"
 #include "simplyp_quad.cuh"
+#include "simplyp_plan.cuh"
 
 using namespace simplyp;
 
@@ -88,23 +89,11 @@ struct KArgs {
                                 // length of the record, i.e. the stride of forcing / obs / out
   int pilot_pass;               // 1: this launch is the pilot (writes cost / hist / carry, no diagnostics, no finalise)
   int* plan;                    // placement of a cost-ordered ensemble on the SMs (PLAN_* below), or null
-  int plan_nsm, plan_ny, plan_np, plan_q;
+  PlanShape shape;              // valid when plan != nullptr
 };
 constexpr int COST_BUCKETS = 4096;
 
-// Placement of a cost-ordered, latency-bound ensemble (2 resident blocks per SM, B virtual blocks of 32 members).
-// The launch has exactly as many blocks as there are lists; a block does not take the virtual block blockIdx.x but
-// claims a LIST by where it lands: the first block to arrive on an SM (%smid) takes the next first-list, the second
-// one the second-list that belongs to it.  With Q = max(0, B - 2 nSM) virtual blocks too many for the machine:
-//   first-list t < nY = nSM - Q : heavy virtual block t;              its second-list: virtual block nY + t (t < nP)
-//   first-list nY + x, x < Q    : light blocks xb+Q+x then B-1-x;     its second-list: light block xb+x
-// where xb = nY + nP and cost_scatter_kernel has laid the members out so that virtual blocks [0, nY) are the heaviest
-// in descending order, [nY, nY+nP) their partners in ASCENDING order (the heaviest block shares its SM with the
-// lightest partner) and [xb, B) the 3Q lightest blocks in descending order (the two blocks that share a slot are
-// taken from the lightest 2Q, a heavier one with a lighter one; the block beside them from the Q above).  So the hardware never queues a block (a queued block starts
-// only when the first resident one ends, 7.6 ms into a 14 ms run at 10^4 members), and the two light blocks that must
-// share a slot run next to a third light block that leaves them the SM early.  Every list is claimed exactly once
-// whatever the placement: a block that cannot have its list takes the last one still free.
+// Placement plan (simplyp_plan.cuh): device-side bookkeeping of the claims, an int array in the workspace.
 constexpr int PLAN_MAX_SM = 1024;                  // %smid is folded into this range
 constexpr int PLAN_FIRST_NEXT = 0;
 constexpr int PLAN_SM_ARR = 16;                    // [PLAN_MAX_SM] blocks that have arrived on the SM
@@ -509,24 +498,10 @@ __global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a
 // ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
 // instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
 enum { MODE_RUN = 0, MODE_CAL = 1 };
-// First virtual block of a list of the placement plan (-1: the list does not exist); lists [0, nSM) are the
-// first-lists, list nSM + t is the second-list of first-list t.
-__device__ __forceinline__ int plan_list_head(const KArgs& a, int list) {
-  const int nY = a.plan_ny, nP = a.plan_np, Q = a.plan_q, xb = nY + nP;
-  if (list < a.plan_nsm) return list < nY ? list : xb + Q + (list - nY);
-  const int t = list - a.plan_nsm;
-  if (t < nY) return t < nP ? nY + t : -1;
-  return t < a.plan_nsm ? xb + (t - nY) : -1;
-}
-// virtual block that follows `vb` in its list, or -1
-__device__ __forceinline__ int plan_list_next(const KArgs& a, int vb) {
-  const int Q = a.plan_q, x = vb - (a.plan_ny + a.plan_np + Q);
-  return (x >= 0 && x < Q) ? a.plan_ny + a.plan_np + 3 * Q - 1 - x : -1;
-}
 // Thread 0 of a block claims a list (see the PLAN_* comment) and returns its first virtual block.
 __device__ int plan_claim(const KArgs& a) {
   int* plan = a.plan;
-  const int nSM = a.plan_nsm;
+  const int nSM = a.shape.n_sm;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   smid &= (PLAN_MAX_SM - 1);
@@ -544,11 +519,11 @@ __device__ int plan_claim(const KArgs& a) {
     do {
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(plan + PLAN_SM_LIST + smid) : "memory");
     } while (v == 0 && clock64() - t0 < (1ll << 20));
-    if (v > 0 && plan_list_head(a, nSM + v - 1) >= 0 && atomicCAS(claimed + nSM + v - 1, 0, 1) == 0) list = nSM + v - 1;
+    if (v > 0 && plan_list_head(a.shape, nSM + v - 1) >= 0 && atomicCAS(claimed + nSM + v - 1, 0, 1) == 0) list = nSM + v - 1;
   }
   for (int l = 2 * nSM - 1; list < 0 && l >= 0; --l)
-    if (plan_list_head(a, l) >= 0 && atomicCAS(claimed + l, 0, 1) == 0) list = l;
-  return list < 0 ? -1 : plan_list_head(a, list);
+    if (plan_list_head(a.shape, l) >= 0 && atomicCAS(claimed + l, 0, 1) == 0) list = l;
+  return list < 0 ? -1 : plan_list_head(a.shape, list);
 }
 
 template <int MODE, int MINB, bool STIFF>
@@ -685,7 +660,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < FORC_SLOTS; ++i) mbar_inval(&ring->full[i]);
-    s_vblock = plan_list_next(a, vblock);
+    s_vblock = plan_list_next(a.shape, vblock);
   }
   __syncthreads();
   vblock = s_vblock;
@@ -919,26 +894,14 @@ __global__ void cost_scan_kernel(unsigned* hist) {
 #pragma unroll
   for (int k = 0; k < PER; ++k) { hist[COST_BUCKETS - 1 - (PER * threadIdx.x + k)] = run; run += loc[k]; }
 }
-// Member layout of a planned launch (PLAN_* comment).  r = rank of the member, heaviest first.
-//  * the `solo` heaviest members each lead a warp of their own whose other seven quads hold light members (the
-//    lightest of the partner region), so that the longest lock-step chain of the launch is one member's step count,
-//    not the per-day maximum over eight similar heavy members;
-//  * the blocks of the partner region [nY, nY + n_rev) are stored in reverse order (lightest first).
-struct MemberLayout { int solo, nY, n_rev, fill_end; };
+// Scatter of the members into their places: rank by the counting sort (heaviest first), place by the member layout
+// of the plan (simplyp_plan.cuh; the identity for an unplanned launch).
 __global__ void cost_scatter_kernel(const unsigned* cost, unsigned* offsets, int* perm, int M, MemberLayout L) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const unsigned c = cost[m];
-  int pos = (int)atomicAdd(&offsets[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);   // rank, heaviest first
-  const int K = L.solo, fill_begin = L.fill_end - 7 * K;
-  if (pos < K) pos = 8 * pos;
-  else if (pos >= fill_begin && pos < L.fill_end) { const int t = pos - fill_begin; pos = 8 * (t / 7) + 1 + t % 7; }
-  else {
-    if (pos < fill_begin) pos += 7 * K;
-    const int blk = pos >> 5;
-    if (blk >= L.nY && blk < L.nY + L.n_rev) pos = ((L.nY + (L.n_rev - 1 - (blk - L.nY))) << 5) | (pos & 31);
-  }
-  perm[pos] = m;
+  const int rank = (int)atomicAdd(&offsets[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+  perm[member_layout_index(rank, L)] = m;
 }
 
 // ------------------------------------------------------------------------------------------ obs constants
@@ -1150,24 +1113,16 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   int dev = 0, n_sm = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const char* e_plan = getenv("SIMPLYP_SM_PLAN");
-  if (quad_minblocks(grid) == 2 && n_sm > 0 && n_sm <= PLAN_MAX_SM && grid > n_sm && dims.n_members >= 2048 &&
-      !(e_plan && atoi(e_plan) == 0)) {
-    const int B = (int)grid, Q = B > 2 * n_sm ? B - 2 * n_sm : 0;
-    const int nY = n_sm - Q, nP = (B - nY - 3 * Q) < nY ? (B - nY - 3 * Q) : nY;
-    if (nY > 0 && nP > 0 && 3 * Q <= B - nY) {
-      int solo = dims.n_members / 400 / 4 * 4;       // one block in about twelve of the heavy blocks
-      if (const char* e = getenv("SIMPLYP_SOLO_WARPS")) { const int v = atoi(e); if (v >= 0) solo = v; }
-      if (8 * solo > 32 * nY || 7 * solo > 16 * nP) solo = 0;
-      lay.solo = solo;
-      lay.nY = nY;
-      lay.n_rev = nP - ((Q == 0 && dims.n_members % 32 != 0) ? 1 : 0);   // a ragged last block stays last
-      const long long pe = 32ll * (nY + nP);
-      lay.fill_end = (int)(pe < dims.n_members ? pe : dims.n_members);
-      int* plan = reinterpret_cast<int*>(ws + L.off_plan);
-      SP_CUDA(cudaMemsetAsync(plan, 0, sizeof(int) * PLAN_INTS, st));
-      a.plan = plan;
-      a.plan_nsm = n_sm; a.plan_ny = nY; a.plan_np = nP; a.plan_q = Q;
-    }
+  PlanShape shape;
+  if (quad_minblocks(grid) == 2 && n_sm <= PLAN_MAX_SM && dims.n_members >= 2048 && !(e_plan && atoi(e_plan) == 0) &&
+      plan_shape(grid, n_sm, shape)) {
+    int solo = dims.n_members / 400 / 4 * 4;         // one block in about twelve of the heavy blocks
+    if (const char* e = getenv("SIMPLYP_SOLO_WARPS")) { const int v = atoi(e); if (v >= 0) solo = v; }
+    lay = member_layout(shape, dims.n_members, solo);
+    int* plan = reinterpret_cast<int*>(ws + L.off_plan);
+    SP_CUDA(cudaMemsetAsync(plan, 0, sizeof(int) * PLAN_INTS, st));
+    a.plan = plan;
+    a.shape = shape;
   }
   cost_scatter_kernel<<<(dims.n_members + 255) / 256, 256, 0, st>>>(p.cost, p.hist, perm, dims.n_members, lay);
   g_launches.fetch_add(3);
@@ -1282,7 +1237,7 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     if (S > 1) simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
     else if (quad_minblocks(grid) == 2) {
       // planned placement: one block per list (n_sm first-lists, n_p + q second-lists), all resident at once
-      const unsigned g = a.plan ? (unsigned)(a.plan_nsm + a.plan_np + a.plan_q) : (unsigned)grid;
+      const unsigned g = a.plan ? (unsigned)a.shape.n_lists() : (unsigned)grid;
       simplyp_quad_kernel<MODE, 2, false><<<g, block, smem, st>>>(a);
     }
     else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);

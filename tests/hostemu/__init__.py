@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "libsimplyp_hostemu.so")
 DEPS = [SRC, os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_core.cuh"),
         os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_thread.cuh"),
         os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_quad.cuh"),
+        os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_plan.cuh"),
         os.path.join(ROOT, "include", "simplyp_b200.h")]
 
 _lib = None
@@ -83,3 +84,42 @@ def exp_tab(x):
     y = np.empty_like(x)
     lib.hostemu_exp_tab(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_int(x.size))
     return y
+
+
+def run_quad_split(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, split):
+    """The quad program over days [0, split) and then, continued from the stored midnight state, [split, D)."""
+    from simplyp_b200 import _cabi, packing as pk
+    lib = load()
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    member_params = np.ascontiguousarray(member_params, dtype=np.float64)
+    sc_params = np.ascontiguousarray(sc_params, dtype=np.float64)
+    if sc_params.ndim == 2:
+        sc_params = sc_params[None]
+    M, D = member_params.shape[0], forcing.shape[0]
+    po = np.ascontiguousarray(parent_offsets, dtype=np.int32)
+    pid = np.zeros(1, dtype=np.int32)
+    dims = _cabi.make_dims(M, 1, D, sc_params.shape[0], 0, 0)
+    out = np.zeros((M, 1, D, pk.NOUT))
+    diag = np.zeros((M, 1, pk.NDIAG), dtype=np.int64)
+    vp = C.c_void_p
+    rc = lib.hostemu_run_quad_split(C.byref(dims), C.byref(opt), forcing.ctypes.data_as(vp),
+                                    member_params.ctypes.data_as(vp), sc_params.ctypes.data_as(vp),
+                                    po.ctypes.data_as(vp), pid.ctypes.data_as(vp), out.ctypes.data_as(vp),
+                                    diag.ctypes.data_as(vp), C.c_int(int(split)))
+    assert rc == 0
+    return out, diag
+
+
+def plan(M, n_sm, solo):
+    """Placement plan arithmetic: (index_of_rank [M], list_of_block [B], pos_in_list [B], (nY, nP, Q, n_lists)) or None."""
+    lib = load()
+    B = (M + 31) // 32
+    idx = np.zeros(M, dtype=np.int32)
+    lst = np.zeros(B, dtype=np.int32)
+    pos = np.zeros(B, dtype=np.int32)
+    shape = np.zeros(4, dtype=np.int32)
+    vp = C.c_void_p
+    rc = lib.hostemu_plan(C.c_int(M), C.c_int(n_sm), C.c_int(solo), idx.ctypes.data_as(vp), lst.ctypes.data_as(vp),
+                          pos.ctypes.data_as(vp), shape.ctypes.data_as(vp))
+    assert rc >= 0, "a virtual block is out of range or sits in two lists"
+    return None if rc == 0 else (idx, lst, pos, tuple(int(x) for x in shape))

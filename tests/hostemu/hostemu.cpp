@@ -9,6 +9,7 @@
 
 #include "../../simplyp_b200/csrc/simplyp_thread.cuh"
 #include "../../simplyp_b200/csrc/simplyp_quad.cuh"
+#include "../../simplyp_b200/csrc/simplyp_plan.cuh"
 
 using namespace simplyp;
 
@@ -115,6 +116,61 @@ extern "C" int hostemu_run_quad(const SimplypDims* dims, const SimplypOptions* o
     }
   }
   return 0;
+}
+
+// One sub-catchment, the record integrated in two launches' worth of pieces: days [0, split) with the midnight state
+// stored (what the cost pilot does), then days [split, D) continued from it (what the main launch does).
+extern "C" int hostemu_run_quad_split(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                                      const double* member_params, const double* sc_params, const int32_t* po,
+                                      const int32_t* pid, double* out, int64_t* diag, int split) {
+  const int M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
+  if (S != 1 || split <= 0 || split >= D) return -1;
+  ThreadOptions t;
+  t.rtol = opt->rtol; t.atol = opt->atol; t.step_len = opt->step_len;
+  t.max_steps_per_day = opt->max_steps_per_day > 0 ? opt->max_steps_per_day : 5000;
+  t.dynamic_epc0 = opt->dynamic_epc0; t.dynamic_erod = opt->dynamic_erodibility;
+  t.run_mode_cal = opt->run_mode_cal; t.strict_quirks = opt->strict_quirks;
+  t.snow_on_device = opt->snow_on_device;
+  std::vector<QuadCarry> carry(M);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int m = 0; m < M; ++m) {
+      const double* mp = member_params + (size_t)m * SIMPLYP_NP_MEMBER;
+      const double* scp = sc_params + (size_t)(Msc > 1 ? m : 0) * SIMPLYP_NP_SC;
+      const double fNCA_last = scp[SIMPLYP_SC_F_AR] * scp[SIMPLYP_SC_F_NC_AR] + scp[SIMPLYP_SC_F_NC_IG] * scp[SIMPLYP_SC_F_IG];
+      const int nc_last = fNCA_last > 0.0 ? 1 : (scp[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
+      HostIO io{forcing, scp, po, pid, out, 1, D, m, 0};
+      QuadHost4 q;
+      QuadMem qm;
+      ThreadCounters cnt;
+      if (pass == 0) run_quad<true>(q, mp, scp, scp[SIMPLYP_SC_A_CATCH], nc_last, t, split, true, qm, io, cnt, 0, nullptr, &carry[m]);
+      else run_quad<true>(q, mp, scp, scp[SIMPLYP_SC_A_CATCH], nc_last, t, D, true, qm, io, cnt, split, &carry[m], nullptr);
+      if (diag && pass == 1) {
+        int64_t* dg = diag + (size_t)m * SIMPLYP_NDIAG;
+        dg[0] = cnt.steps; dg[1] = cnt.rejected; dg[2] = cnt.rhs_evals; dg[3] = cnt.status;
+      }
+    }
+  return 0;
+}
+
+// Placement plan arithmetic (simplyp_plan.cuh) for M members on n_sm SMs: item index of every cost rank, and for
+// every virtual block the list that runs it and its position in that list.  Returns 0 if the plan does not apply.
+extern "C" int hostemu_plan(int M, int n_sm, int solo, int* index_of_rank, int* list_of_block, int* pos_in_list,
+                            int* shape4) {
+  PlanShape p;
+  const long long B = ((long long)M + 31) / 32;
+  if (!plan_shape(B, n_sm, p)) return 0;
+  shape4[0] = p.nY; shape4[1] = p.nP; shape4[2] = p.Q; shape4[3] = p.n_lists();
+  const MemberLayout L = member_layout(p, M, solo);
+  for (int r = 0; r < M; ++r) index_of_rank[r] = member_layout_index(r, L);
+  for (int b = 0; b < (int)B; ++b) { list_of_block[b] = -1; pos_in_list[b] = -1; }
+  for (int l = 0; l < 2 * n_sm; ++l) {
+    int pos = 0;
+    for (int vb = plan_list_head(p, l); vb >= 0; vb = plan_list_next(p, vb), ++pos) {
+      if (vb >= (int)B || list_of_block[vb] != -1) return -1;      // out of range or claimed twice
+      list_of_block[vb] = l; pos_in_list[vb] = pos;
+    }
+  }
+  return 1;
 }
 
 // The quad formulation of ode_f against the scalar rhs() at one state: returns the largest relative

@@ -87,3 +87,48 @@ def test_stiff_reach_takes_the_rosenbrock_path(area):
 @pytest.mark.parametrize("prog", ["quad", "scalar"])
 def test_against_the_reference_shipped_csvs(golden_dir, prog):
     parity.check_shipped_golden(RUNNERS[prog], golden_dir)
+
+
+def test_record_continued_from_a_stored_midnight_state_is_bitwise_the_same():
+    """The cost pilot integrates the first days of the record and hands every member's midnight state to the main
+    launch (QuadCarry): days [0, k) + [k, D) must give exactly the bits of [0, D) — outputs and counters."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load("2004-01-01", "2004-03-10", dynamic="y")
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(6, seed=5)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    want, dg = hostemu.run_quad(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    for split in (1, 8, 37):
+        got, dg2 = hostemu.run_quad_split(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt, split)
+        assert np.array_equal(got, want) and np.array_equal(dg2, dg), split
+
+
+@pytest.mark.parametrize("n_sm", [148, 132])
+def test_placement_plan_covers_every_member_and_block_once(n_sm):
+    """Arithmetic of the planned placement (simplyp_plan.cuh): for every ensemble size in the planned range the member
+    layout is a permutation, every virtual block sits in exactly one list, only the Q overflow lists hold two blocks,
+    the launch has one block per list, and the heaviest block's partner is the lightest of the partner region."""
+    for M in (32 * n_sm + 1, 4800, 6001, 32 * 2 * n_sm - 7, 32 * 2 * n_sm, 32 * 2 * n_sm + 1, 9500, 10000,
+              32 * (2 * n_sm + n_sm // 4)):
+        B = (M + 31) // 32
+        for solo in (0, 24):
+            res = hostemu.plan(M, n_sm, solo)
+            if B <= n_sm:
+                assert res is None
+                continue
+            idx, lst, pos, (nY, nP, Q, n_lists) = res
+            assert np.array_equal(np.sort(idx), np.arange(M)), (M, solo)              # a permutation of the members
+            assert Q == max(0, B - 2 * n_sm) and nY == n_sm - Q and nY + nP + 3 * Q == B
+            assert (lst >= 0).all() and len(np.unique(lst)) == n_lists == n_sm + nP + Q
+            counts = np.bincount(lst, minlength=2 * n_sm)
+            assert (counts[:nY] == 1).all() and (counts[nY:n_sm] == 2).all() and counts.max() <= 2
+            assert sorted(pos[lst == nY].tolist()) == ([0, 1] if Q else sorted(pos[lst == nY].tolist()))
+            # rank 0 leads virtual block 0; its partner block (list n_sm + 0) holds the lightest ranks of the partner region
+            assert idx[0] == 0
+            partner_block = int(np.where(lst == n_sm)[0][0])
+            ranks_in_partner = np.where(idx // 32 == partner_block)[0]
+            other = np.where(lst == n_sm + nP - 1)[0]
+            if nP > 1 and solo == 0 and not (Q == 0 and M % 32):
+                assert ranks_in_partner.min() > np.where(idx // 32 == int(other[0]))[0].max()
