@@ -553,120 +553,120 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   QuadMem* qmem = reinterpret_cast<QuadMem*>(smem_cold);
   ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)quads_per_block * (sizeof(QuadMem) / sizeof(double)));
   for (;;) {                                       // one pass per virtual block of a claimed list (else one pass)
-  if (threadIdx.x == 0) {
-    ring->n_consumers = blockDim.x >> 5;          // the warps of the block
-    for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < FORC_SLOTS; ++i)
-      if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
-  }
-  __syncthreads();
-
-  long long idx = (long long)vblock * quads_per_block + (threadIdx.x >> 2);
-  bool valid;
-  int w, m;
-  if (a.level_item_off == nullptr) {               // one sub-catchment: items are the members
-    valid = idx < a.M;
-    if (!valid) idx = a.M - 1;                     // padding quads shadow the last item and write nothing
-    w = 0;
-    m = a.perm ? a.perm[idx] : (int)idx;
-  } else {
-    if (idx >= a.n_items_padded) idx = a.n_items_padded - 1;
-    int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (a.level_item_off[mid] <= idx) lo = mid; else hi = mid;
+    if (threadIdx.x == 0) {
+      ring->n_consumers = blockDim.x >> 5;          // the warps of the block
+      for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int i = 0; i < FORC_SLOTS; ++i)
+        if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
     }
-    long long local = idx - a.level_item_off[lo];
-    const int o0 = a.level_order_off[lo];
-    const long long n_real = (long long)(a.level_order_off[lo + 1] - o0) * a.M;
-    valid = local < n_real;
-    if (!valid) local = n_real - 1;
-    const int wl = (int)(local / a.M);
-    w = o0 + wl;
-    m = (int)(local - (long long)wl * a.M);
-  }
-  const int s = a.work_sc ? a.work_sc[w] : w;
+    __syncthreads();
 
-  const double* mp = a.member_params + (size_t)m * SIMPLYP_NP_MEMBER;
-  const double* scp = a.sc_params + (size_t)(a.Msc > 1 ? m : 0) * a.S * SIMPLYP_NP_SC;
-  const double* sp = scp + (size_t)s * SIMPLYP_NP_SC;
-  const double A_qr0 = scp[(size_t)a.sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-  const double* spl = scp + (size_t)(a.S - 1) * SIMPLYP_NP_SC;
-  const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
-  const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
-
-  // calibration: shared-memory accumulators of the fit statistics, behind the forcing ring
-  const bool resume = a.carry != nullptr && !a.pilot_pass;
-  const QuadCarry* cin = resume ? a.carry + m : nullptr;
-  QuadCarry* cout = a.pilot_pass ? a.carry + m : nullptr;
-  double* sacc = nullptr;
-  if (MODE == MODE_CAL) {
-    sacc = reinterpret_cast<double*>(ring + 1) + (size_t)(threadIdx.x >> 2) * STAT_STRIDE;
-    if ((threadIdx.x & 3) == 0) {
-      const double* src = resume ? a.carry_stats + (size_t)m * (STAT_SLOTS * 8) : nullptr;
-      for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = src ? src[i] : 0.0;
-    }
-    __syncwarp();
-  }
-  QuadDev q;
-  q.ql = threadIdx.x & 3;
-  q.tab = s_exp2tab;
-  QuadMem& qm = qmem[threadIdx.x >> 2];
-  ThreadCounters cnt;
-  if (MODE == MODE_CAL) {
-    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
-    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
-    if (valid && q.ql == 0) {
-      if (a.pilot_pass) {
-        double* dst = a.carry_stats + (size_t)m * (STAT_SLOTS * 8);
-        for (int i = 0; i < STAT_SLOTS * 8; ++i) dst[i] = sacc[i];
-      } else {
-        io.finalise();
+    long long idx = (long long)vblock * quads_per_block + (threadIdx.x >> 2);
+    bool valid;
+    int w, m;
+    if (a.level_item_off == nullptr) {               // one sub-catchment: items are the members
+      valid = idx < a.M;
+      if (!valid) idx = a.M - 1;                     // padding quads shadow the last item and write nothing
+      w = 0;
+      m = a.perm ? a.perm[idx] : (int)idx;
+    } else {
+      if (idx >= a.n_items_padded) idx = a.n_items_padded - 1;
+      int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.level_item_off[mid] <= idx) lo = mid; else hi = mid;
       }
+      long long local = idx - a.level_item_off[lo];
+      const int o0 = a.level_order_off[lo];
+      const long long n_real = (long long)(a.level_order_off[lo + 1] - o0) * a.M;
+      valid = local < n_real;
+      if (!valid) local = n_real - 1;
+      const int wl = (int)(local / a.M);
+      w = o0 + wl;
+      m = (int)(local - (long long)wl * a.M);
     }
-    cnt.status |= io.wait_status;
-  } else {
-    RunIO io(a, m, s, ring);
-    run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
-    cnt.status |= io.wait_status;
-  }
-  if (a.pilot_pass) {                                // the pilot's product: the cost of every member
-    if (valid && q.ql == 0) {
-      const unsigned c = (unsigned)cnt.steps;
-      a.cost[m] = c;
-      atomicAdd(&a.hist[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+    const int s = a.work_sc ? a.work_sc[w] : w;
+
+    const double* mp = a.member_params + (size_t)m * SIMPLYP_NP_MEMBER;
+    const double* scp = a.sc_params + (size_t)(a.Msc > 1 ? m : 0) * a.S * SIMPLYP_NP_SC;
+    const double* sp = scp + (size_t)s * SIMPLYP_NP_SC;
+    const double A_qr0 = scp[(size_t)a.sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    const double* spl = scp + (size_t)(a.S - 1) * SIMPLYP_NP_SC;
+    const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
+    const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
+
+    // calibration: shared-memory accumulators of the fit statistics, behind the forcing ring
+    const bool resume = a.carry != nullptr && !a.pilot_pass;
+    const QuadCarry* cin = resume ? a.carry + m : nullptr;
+    QuadCarry* cout = a.pilot_pass ? a.carry + m : nullptr;
+    double* sacc = nullptr;
+    if (MODE == MODE_CAL) {
+      sacc = reinterpret_cast<double*>(ring + 1) + (size_t)(threadIdx.x >> 2) * STAT_STRIDE;
+      if ((threadIdx.x & 3) == 0) {
+        const double* src = resume ? a.carry_stats + (size_t)m * (STAT_SLOTS * 8) : nullptr;
+        for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = src ? src[i] : 0.0;
+      }
+      __syncwarp();
     }
-    return;
-  }
-  if (a.diag && valid && q.ql == 0) {
-    long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
-    dg[SIMPLYP_DG_STEPS] = cnt.steps;
-    dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
-    dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
-    dg[SIMPLYP_DG_STATUS] = cnt.status;
+    QuadDev q;
+    q.ql = threadIdx.x & 3;
+    q.tab = s_exp2tab;
+    QuadMem& qm = qmem[threadIdx.x >> 2];
+    ThreadCounters cnt;
+    if (MODE == MODE_CAL) {
+      CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
+      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+      if (valid && q.ql == 0) {
+        if (a.pilot_pass) {
+          double* dst = a.carry_stats + (size_t)m * (STAT_SLOTS * 8);
+          for (int i = 0; i < STAT_SLOTS * 8; ++i) dst[i] = sacc[i];
+        } else {
+          io.finalise();
+        }
+      }
+      cnt.status |= io.wait_status;
+    } else {
+      RunIO io(a, m, s, ring);
+      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+      cnt.status |= io.wait_status;
+    }
+    if (a.pilot_pass) {                                // the pilot's product: the cost of every member
+      if (valid && q.ql == 0) {
+        const unsigned c = (unsigned)cnt.steps;
+        a.cost[m] = c;
+        atomicAdd(&a.hist[c < COST_BUCKETS ? c : COST_BUCKETS - 1], 1u);
+      }
+      return;
+    }
+    if (a.diag && valid && q.ql == 0) {
+      long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
+      dg[SIMPLYP_DG_STEPS] = cnt.steps;
+      dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
+      dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
+      dg[SIMPLYP_DG_STATUS] = cnt.status;
 #ifdef SP_TIMELINE                                  // analysis builds (scripts/exp_timeline.py): when and where the warp ran
-    unsigned long long t1; unsigned smid;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    dg[SIMPLYP_DG_REJECTED] = (long long)sp_timeline_t0;
-    dg[SIMPLYP_DG_RHS] = (long long)t1;
-    dg[SIMPLYP_DG_STATUS] = (long long)smid | ((long long)vblock << 16) | ((long long)(threadIdx.x >> 5) << 40) |
-                            ((long long)cnt.rejected << 44);      // cnt.rejected holds the warp's lock-step attempts here
+      unsigned long long t1; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      dg[SIMPLYP_DG_REJECTED] = (long long)sp_timeline_t0;
+      dg[SIMPLYP_DG_RHS] = (long long)t1;
+      dg[SIMPLYP_DG_STATUS] = (long long)smid | ((long long)vblock << 16) | ((long long)(threadIdx.x >> 5) << 40) |
+                              ((long long)cnt.rejected << 44);      // cnt.rejected holds the warp's lock-step attempts here
 #endif
-  }
-  if (!(PLAN && a.plan != nullptr)) break;
-  // next virtual block of the list: every warp has left the forcing ring and the shared-memory state of its quads
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < FORC_SLOTS; ++i) mbar_inval(&ring->full[i]);
-    s_vblock = plan_list_next(a.shape, vblock);
-  }
-  __syncthreads();
-  vblock = s_vblock;
-  if (vblock < 0) break;
+    }
+    if (!(PLAN && a.plan != nullptr)) break;
+    // next virtual block of the list: every warp has left the forcing ring and the shared-memory state of its quads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < FORC_SLOTS; ++i) mbar_inval(&ring->full[i]);
+      s_vblock = plan_list_next(a.shape, vblock);
+    }
+    __syncthreads();
+    vblock = s_vblock;
+    if (vblock < 0) break;
 #ifdef SP_TIMELINE
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sp_timeline_t0));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sp_timeline_t0));
 #endif
   }
 }
