@@ -327,7 +327,9 @@ def run_ours(args):
                                    "log-likelihood vs observed Q and TDP, Dynamic_EPC0/erodibility on" % (args.period, D, M_local),
                        "members_total": M_total, "days": D, "sub_catchments": S, "obs_series": [list(l) for l in w["labels"]],
                        "rtol": opt.rtol, "atol": opt.atol, "parallelism": "ensemble members sharded over %d GPU(s)" % world,
-                       "l2": "256 MB buffer written between timed steps (outside the per-step CUDA events)"},
+                       "l2": "256 MB buffer written between timed steps (outside the per-step CUDA events)",
+                       "launches_per_step": "pilot pass (days 0-7, member order) + counting sort (2) + observation "
+                                            "constants + main pass (days 8-end, cost order, blocks placed by SM)"},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "simplyp_calibrate_host (C-ABI, pinned host buffers)", "matches_device_leg": same},
