@@ -40,8 +40,6 @@ def parse_args():
     ap.add_argument("--period", default="2004", choices=["2004", "full"])
     ap.add_argument("--rtol", type=float, default=None)
     ap.add_argument("--atol", type=float, default=None)
-    ap.add_argument("--lanes", type=int, default=0, choices=[0, 1, 4],
-                    help="lanes per (member, sub-catchment): 0/4 = quad kernel (default), 1 = one thread per item")
     ap.add_argument("--pilot-days", type=int, default=0, help="cost pilot: 0 = library default, -1 = off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
@@ -216,10 +214,9 @@ def run_ours(args):
     M_total = M_local * world
     w = build_workload(args.period, M_total)
     lo, hi = ens.shard_bounds(M_total, world, rank)
-    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol,
-                           lanes_per_item=args.lanes)
+    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol)
     opt.pilot_days = args.pilot_days
-    kernel_name = "simplyp_integrate_kernel<cal>" if args.lanes == 1 else "simplyp_quad_kernel<cal>"
+    kernel_name = "simplyp_quad_kernel<cal>"
     eng = Engine(local_rank)
     S, D, V = w["topo"].n_sc, w["forcing"].shape[0], w["obs_m"].shape[0]
 

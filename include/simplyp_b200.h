@@ -18,9 +18,13 @@
  * Conventions
  *  - plain C, no torch/STL types; all arrays are dense, row-major, IEEE fp64 unless stated;
  *  - "_device" entry points take DEVICE pointers owned by the caller and enqueue on `stream`
- *    (a cudaStream_t passed as void*; NULL = legacy default stream) without synchronising;
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream) without synchronising, so they can be
+ *    overlapped with copies and captured into a CUDA graph (the host-side topology arrays are copied into
+ *    pinned images the library keeps until simplyp_release_cache(); a call with a topology it has not seen
+ *    allocates such an image, so issue one ordinary call before capturing in the strict capture mode);
  *  - "_host" entry points take HOST pointers, copy H2D, run, copy D2H and synchronise
- *    (this is what a reference-side caller that holds numpy arrays uses);
+ *    (this is what a reference-side caller that holds numpy arrays uses); their device buffers are cached
+ *    PER DEVICE behind a per-device lock: one host thread per device runs concurrently with the others;
  *  - every entry point returns 0 on success or a negative SIMPLYP_E* code and never throws;
  *    simplyp_last_error() gives the message of the calling thread's last failure;
  *  - there is NO CPU fallback: without a CUDA device every compute entry point returns
@@ -35,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SIMPLYP_ABI_VERSION 2
+#define SIMPLYP_ABI_VERSION 3
 
 /* error codes */
 #define SIMPLYP_OK          0
@@ -176,9 +180,9 @@ typedef struct SimplypOptions {
   int32_t run_mode_cal;      /* p_SU.run_mode == 'cal': Kf derived per SC (model.py:449-451) */
   int32_t sc_qr0;            /* 0-based index of p['SC_Qr0'] in the run order */
   int32_t strict_quirks;     /* 1: replicate the leaked NC_type of model.py:442,676 */
-  int32_t threads_per_block; /* 0 = library default (scalar kernel only) */
-  int32_t lanes_per_item;    /* lanes that integrate one (member, sub-catchment): 0 = default (4, the quad
-                                kernel), 4, or 1 (one thread per item, the round-1 kernel kept for A/B runs) */
+  int32_t threads_per_block; /* reserved (0) */
+  int32_t lanes_per_item;    /* lanes that integrate one (member, sub-catchment): 0 (default) or 4 — the quad kernel;
+                                the round-1 one-thread-per-item kernel (1) was retired and is refused */
   int32_t pilot_days;        /* ensembles of one sub-catchment: the first `pilot_days` days are integrated in member
                                 order by a pilot launch whose step counts order the members over the lock-step warps;
                                 the main launch continues from its midnight state (0 = default 8, < 0 = no pilot;
@@ -258,7 +262,7 @@ int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOpt
                            const double* obs, const int32_t* obs_desc,
                            double* stats, int64_t* diag);
 
-/* Releases the device buffers cached by the _host entry points. */
+/* Releases the device buffers cached by the _host entry points (all devices) and the pinned topology images. */
 void simplyp_release_cache(void);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */

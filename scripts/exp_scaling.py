@@ -14,7 +14,7 @@ def main():
         w = bench.build_workload("2004", M)
         d = [eng.to_device(w[k]) for k in ("forcing", "member", "sc", "obs_m", "desc")]
         for tb in blocks:
-            opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], threads_per_block=tb)
+            opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"])
             for _ in range(2):
                 st, dg = eng.calibrate(d[0], d[1], d[2], w["topo"].parent_offsets, w["topo"].parent_ids, d[3], d[4], opt)
             torch.cuda.synchronize()

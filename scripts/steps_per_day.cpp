@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
-#include "../simplyp_b200/csrc/simplyp_thread.cuh"
+#include "../tests/hostemu/scalar_program.h"
 using namespace simplyp;
 struct IO {
   const double* f; const ThreadCounters* cnt; uint16_t* steps; long long last;

@@ -89,7 +89,7 @@ def load():
     lib.simplyp_thornthwaite_pet_device.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, vp,
                                                     C.c_int32, vp]
     lib.simplyp_thornthwaite_pet_device.restype = C.c_int
-    if lib.simplyp_abi_version() != 2:
+    if lib.simplyp_abi_version() != 3:
         raise SimplypError("ABI version mismatch")
     _lib = lib
     return lib

@@ -9,10 +9,10 @@
 // Reference map (all line numbers: Current_Release/v0-2A/simplyP/model.py):
 //   gate()            f_x                         :23-37
 //   soilp_update()    discretized_soilP           :39-56
-//   rhs()             ode_f                       :58-187
+//   (ode_f itself, :58-187, is quad_rhs() in simplyp_quad.cuh)
 //   setup_thread()    run_simply_p, setup part    :318-335, :349, :377-463, :469
 //   begin_day()       run_simply_p, pre-ODE part  :497-501, :549-594, :600-611, :618
-//   dp5_attempt()     one embedded RK5(4) step attempt; replaces scipy.integrate.odeint (LSODA), :640
+//   kRK, step_factor_sq()  tableau and controller of the embedded pair that replaces scipy.integrate.odeint, :640
 //   end_day()         run_simply_p, post-ODE part :643-724
 #pragma once
 
@@ -34,11 +34,9 @@ namespace simplyp {
 // number of live ODE states and of daily accumulators (ode_f's y[0..11] split by role)
 //   live: VsA VsS Vg Vr Qr Msus TDPr PPr      (y[0..4], y[6], y[8], y[10])
 //   acc : Qr_av Msus_out TDPr_out PPr_out     (y[5], y[7], y[9], y[11]); zero at day start (:618)
-//   The reach volume Vr is NOT integrated: ode_f's dVr/dt = net and dQr/dt = net*a_Q*Qr^b_Q*86400/((1-b_Q)*L)
-//   (:127-131) imply d/dt[Vr - L/(a_Q*86400) * Qr^(1-b_Q)] = 0, and the reference's initial condition
-//   Vr0 = L/(a_Q*Qr0^b_Q*86400)*Qr0 (:457-459) lies on that curve, so Vr == L/(a_Q*86400)*Qr^(1-b_Q) for all t.
-//   The kernel carries Qr only, uses Qr/Vr = (a_Q*86400/L)*Qr^b_Q in the mass equations and reports
-//   Vr from the identity (the LSODA oracle integrates Vr; both agree to the solver tolerance).
+//   The day-boundary code exchanges Qr (not the quad program's u = ln Qr); the reach volume follows
+//   Vr == L/(a_Q*86400)*Qr^(1-b_Q), which ode_f's dVr/dt = net and dQr/dt = net*a_Q*Qr^b_Q*86400/((1-b_Q)*L)
+//   (:127-131) conserve and the reference's initial condition (:457-459) satisfies (reach_volume()).
 constexpr int NL = 7;
 constexpr int NA = 4;
 enum { iVsA = 0, iVsS, iVg, iQr, iMsus, iTDPr, iPPr };
@@ -83,6 +81,19 @@ struct Flags {
   int nc_is_A;       // NC land takes arable hydrology inside ode_f (:113)
   int nc_is_S;       // NC land is semi-natural (:429, :608)
   int post_nc_is_A;  // which hydrology the post-ODE soil-P step uses (:442, :676; leaked variable)
+};
+
+// Run options and per-item counters shared by the kernels and the program (SimplypOptions, narrowed).
+struct ThreadOptions {
+  double rtol, atol, step_len;
+  int max_steps_per_day;
+  int dynamic_epc0, dynamic_erod, run_mode_cal, strict_quirks;
+  int snow_on_device;   // forcing carries raw precipitation and T_air, snow is a per-member scan
+};
+
+struct ThreadCounters {
+  long long steps, rejected, rhs_evals;
+  int status;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -277,44 +288,6 @@ SP_HD double sp_clamp01(double u) {
 SP_HD double gate(double u) {
   u = sp_clamp01(u);
   return u * u * fma(-2.0, u, 3.0);
-}
-
-// ------------------------------------------------------------------------------------------
-// ode_f: derivatives of the 8 live states; the 4 accumulator derivatives come out separately.
-SP_HD void rhs(const Hot& c, const double (&y)[NL], double (&dy)[NL], double (&da)[NA]) {
-  const double VsA = y[iVsA], VsS = y[iVsS], Vg = y[iVg], Qr = y[iQr];
-  // soil boxes (:105-110)
-  const double xA = VsA - c.fc, xS = VsS - c.fc;
-  const double QsA = xA * gate(xA * c.inv_fcd) * c.inv_TsA;
-  const double QsS = xS * gate(xS * c.inv_fcd) * c.inv_TsS;
-  dy[iVsA] = c.Pin - c.aE * (1.0 - sp_exp_core(-c.mu * VsA)) - QsA;
-  dy[iVsS] = c.Pin - c.aE * (1.0 - sp_exp_core(-c.mu * VsS)) - QsS;
-  // groundwater (:121-124)
-  const double xg = Vg * c.inv_Tg - c.Qg_min;
-  const double Qg = c.Qg_min + gate(xg * c.inv_Qgd) * xg;
-  const double soil = c.fA * QsA + c.fS * QsS;
-  dy[iVg] = c.beta * soil - Qg;
-  // reach (:127-132); Qr^b_Q and Qr^k_M share one logarithm
-  const double net = c.qin0 + (1.0 - c.beta) * soil + Qg - Qr;
-  const double lq = sp_log(Qr);
-  const double qb = sp_exp_core(c.bQ * lq);
-  const double qk = sp_exp_core(c.kM * lq);
-  dy[iQr] = net * c.kQ * qb;
-  da[0] = Qr;
-  // outflow rate of the reach, 1/day: Qr/Vr with Vr on its invariant curve
-  const double r = c.cR * qb;
-  // sediment (:138-147)
-  const double oM = y[iMsus] * r;
-  dy[iMsus] = c.cM * qk + c.MsusUS - oM;
-  da[1] = oM;
-  // TDP (:154-168)
-  const double oT = y[iTDPr] * r;
-  dy[iTDPr] = c.tA * QsA + c.tS * QsS + c.tG * Qg + c.t0 - oT;
-  da[2] = oT;
-  // PP (:171-180)
-  const double oP = y[iPPr] * r;
-  dy[iPPr] = c.cP * qk + c.PPUS - oP;
-  da[3] = oP;
 }
 
 // Reach volume on the invariant curve (reported as the 'Vr' output column).
@@ -543,15 +516,7 @@ SP_HD void end_day(const Hot& h, Cold& c, const Flags& fl, int dynamic_epc0, con
 }
 
 // ------------------------------------------------------------------------------------------
-// Embedded explicit Runge-Kutta 5(4) with FSAL (Tsitouras' pair; -DSP_DOPRI5 selects Dormand-Prince).
-// The accumulators are pure quadratures (the RHS does not depend
-// on them), so their stage derivatives are folded into two running sums (5th-order weights and
-// error weights) instead of being stored per stage.
-struct RK {
-  double k1[NL];   // derivative at the current (t, y): reused after a rejection, FSAL after acceptance
-  double a1[NA];   // accumulator derivatives at the current point
-};
-
+// Embedded explicit Runge-Kutta 5(4) with FSAL: Tsitouras' pair (-DSP_DOPRI5 selects Dormand-Prince).
 namespace dp {
 #ifndef SP_DOPRI5
 // Tsitouras 5(4) (Ch. Tsitouras, Comput. Math. Appl. 62 (2011) 770-775): same 7-stage FSAL structure as
@@ -589,110 +554,6 @@ SP_CONST double kRK[RK_N] = {
     dp::a21, dp::a31, dp::a32, dp::a41, dp::a42, dp::a43, dp::a51, dp::a52, dp::a53, dp::a54,
     dp::a61, dp::a62, dp::a63, dp::a64, dp::a65, dp::b1, dp::b2, dp::b3, dp::b4, dp::b5, dp::b6,
     dp::e1, dp::e2, dp::e3, dp::e4, dp::e5, dp::e6, dp::e7};
-
-// One step attempt of size hh from (y, acc).  On return ynew/accnew hold the 5th-order solution,
-// k7/a7 the derivative there, and the return value is the scaled RMS error (<= 1 accepts);
-// a non-finite error is returned as +inf.
-// Stage derivatives k2..k5 of the live states, parked between stages.  They stay in registers: a
-// shared-memory variant ([stage][state][thread] columns, 168 registers, 3 blocks/SM) was measured 8 % slower
-// at 1.6e5 members and 75 % slower at 1e4 members (spills + LDS latency on the critical path).
-struct RegStages {
-  double k[4][NL];
-  SP_HD double ld(int j, int i) const { return k[j][i]; }
-  SP_HD void st(int j, int i, double v) { k[j][i] = v; }
-};
-
-template <class KS>
-SP_HD double dp5_attempt(const Hot& c, const double (&y)[NL], const double (&acc)[NA], const RK& rk, double hh,
-                         double rtol, double atol, double (&ynew)[NL], double (&accnew)[NA], double (&k7)[NL],
-                         double (&a7)[NA], KS& ks) {
-  using namespace dp;
-  double kk[NL], yt[NL], da[NA];
-  double sb[NA], se[NA];
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] = b1 * rk.a1[i]; se[i] = e1 * rk.a1[i]; }
-
-  // stage 2
-#pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a21 * rk.k1[i]);
-  rhs(c, yt, kk, da);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) ks.st(0, i, kk[i]);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] += b2 * da[i]; se[i] += e2 * da[i]; }
-  // stage 3
-#pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a31 * rk.k1[i] + a32 * kk[i]);
-  rhs(c, yt, kk, da);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) ks.st(1, i, kk[i]);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] += b3 * da[i]; se[i] += e3 * da[i]; }
-  // stage 4
-#pragma unroll
-  for (int i = 0; i < NL; ++i) yt[i] = y[i] + hh * (a41 * rk.k1[i] + a42 * ks.ld(0, i) + a43 * kk[i]);
-  rhs(c, yt, kk, da);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) ks.st(2, i, kk[i]);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] += b4 * da[i]; se[i] += e4 * da[i]; }
-  // stage 5
-#pragma unroll
-  for (int i = 0; i < NL; ++i)
-    yt[i] = y[i] + hh * (a51 * rk.k1[i] + a52 * ks.ld(0, i) + a53 * ks.ld(1, i) + a54 * kk[i]);
-  rhs(c, yt, kk, da);
-#pragma unroll
-  for (int i = 0; i < NL; ++i) ks.st(3, i, kk[i]);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] += b5 * da[i]; se[i] += e5 * da[i]; }
-  // stage 6
-#pragma unroll
-  for (int i = 0; i < NL; ++i)
-    yt[i] = y[i] + hh * (a61 * rk.k1[i] + a62 * ks.ld(0, i) + a63 * ks.ld(1, i) + a64 * ks.ld(2, i) + a65 * kk[i]);
-  rhs(c, yt, kk, da);
-#pragma unroll
-  for (int i = 0; i < NA; ++i) { sb[i] += b6 * da[i]; se[i] += e6 * da[i]; }
-  // 5th-order solution and the part of the error estimate that does not need k7 (kk holds k6)
-  double ee[NL];
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    const double k2 = ks.ld(0, i), k3 = ks.ld(1, i), k4 = ks.ld(2, i), k5 = ks.ld(3, i);
-    ynew[i] = y[i] + hh * (b1 * rk.k1[i] + b2 * k2 + b3 * k3 + b4 * k4 + b5 * k5 + b6 * kk[i]);
-    ee[i] = e1 * rk.k1[i] + e2 * k2 + e3 * k3 + e4 * k4 + e5 * k5 + e6 * kk[i];
-  }
-  rhs(c, ynew, k7, a7);
-
-  double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < NL; ++i) {
-    const double err = hh * (ee[i] + e7 * k7[i]);
-    const double sc = atol + rtol * sp_max(fabs(y[i]), fabs(ynew[i]));
-    const double q = err * sp_rcp_fast(sc);
-    s += q * q;
-  }
-#pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    accnew[i] = acc[i] + hh * sb[i];
-    const double err = hh * (se[i] + e7 * a7[i]);
-    const double sc = atol + rtol * sp_max(fabs(acc[i]), fabs(accnew[i]));
-    const double q = err * sp_rcp_fast(sc);
-    s += q * q;
-  }
-  const double en = sqrt(s * (1.0 / (NL + NA)));
-  return (en == en) ? en : INFINITY;   // NaN -> reject
-}
-
-// Step-size factor of the elementary controller for a 5(4) pair: 0.9*err^(-1/5) in [0.2, 5].
-SP_HD double step_factor(double en) {
-  if (!(en > 1e-30)) return 5.0;
-  if (!(en < 1e30)) return 0.2;
-#if defined(__CUDA_ARCH__)
-  const double f = 0.9 * (double)exp2f(-0.2f * __log2f((float)en));
-#else
-  const double f = 0.9 * exp(-0.2 * log(en));
-#endif
-  return sp_min(5.0, sp_max(0.2, f));
-}
 
 // The same controller on the MEAN SQUARE of the scaled error (no square root): 0.9*(en^2)^(-1/10) in [0.2, 5].
 // Device: fp32 lg2/ex2 with flush-to-zero and no range branches — an underflowing en^2 gives lg2 = -inf, hence

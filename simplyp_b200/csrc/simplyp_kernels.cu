@@ -1,12 +1,18 @@
 // simplyp_kernels.cu — sm_100a kernels and the C-ABI of simplyp_b200 (see include/simplyp_b200.h).
 //
 // Kernels
-//   simplyp_integrate_kernel<CAL>   K1 (+K1b routing, K2 output writer or K3 fused statistics):
-//                                   one thread per (ensemble member, sub-catchment); replaces the
-//                                   reference's SC x day loop body, model.py:365-724
-//   obs_const_kernel                observation-only constants of the fit statistics
-//                                   (visualise_results.py:441-449 denominators)
-//   fp64_peak_kernel                DFMA throughput probe for the roofline denominator
+//   simplyp_quad_kernel<MODE,MINB,STIFF>  K1 (+K1a TMA forcing ring, K1b reach routing, K2 output writer or K3 fused
+//                                   statistics): a quad of 4 lanes per (ensemble member, sub-catchment), 8 quads per
+//                                   warp in day lock-step; replaces the reference's SC x day loop body,
+//                                   model.py:365-724 (program: simplyp_quad.cuh, day-boundary algebra: simplyp_core.cuh)
+//   stiff_group_kernel              per-reach stiffness estimate that orders the reaches of a level (device side, so
+//                                   that the *_device entry points never synchronise)
+//   cost_scan_kernel, cost_scatter_kernel  counting sort of the pilot costs (member order of an ensemble)
+//   obs_const_kernel, obs_rank_kernel, spearman_kernel  observation constants / Spearman's r of
+//                                   goodness_of_fit_stats (visualise_results.py:441-449)
+//   waterbody_kernel                sum_to_waterbody (model.py:851-900)
+//   thornthwaite_kernel             daily_PET (inputs.py:232-312)
+//   fp64_peak_kernel, fp64_latency_kernel  DFMA throughput / latency probes for the roofline denominator
 //
 // There is deliberately no host implementation of the integration in this library.
 #include <cuda_runtime.h>
@@ -16,9 +22,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
-#include "simplyp_thread.cuh"
 #include "simplyp_quad.cuh"
 #include "simplyp_plan.cuh"
 
@@ -72,8 +78,7 @@ struct KArgs {
   // 8 items so that the 8 quads of a lock-step warp never depend on each other
   const long long* level_item_off;  // [n_levels+1] padded cumulative item counts
   const int* level_order_off;       // [n_levels+1] offsets into work_sc
-  int n_levels;
-  long long n_items_padded;
+  int n_levels;                     // the padded item total is level_item_off[n_levels] (device side)
   // cost ordering of an ensemble (quad kernel, one sub-catchment): a short pilot run counts the step attempts
   // of every member; members are then dealt to the lock-step warps heaviest first
   double* sim_obs;              // cal + rank statistics: [M][V][D] simulated value on observed days, or null
@@ -120,8 +125,10 @@ constexpr int FORC_SLOTS = 4;     // ring depth (16 KB per block)
 struct ForcingRing {
   double tiles[FORC_SLOTS][FORC_TILE * SIMPLYP_NF];
   unsigned long long full[FORC_SLOTS];   // mbarriers
-  unsigned left[FORC_SLOTS];             // threads that have left the tile currently held by the slot
+  unsigned left[FORC_SLOTS];             // warps that have left the tile currently held by the slot
   unsigned n_consumers;
+  int first_tile;                        // tile of the first day this launch integrates (slot = (tile - first) % SLOTS)
+  int end_day;                           // one past the last day this launch reads: no tile at or beyond it is fetched
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -167,45 +174,26 @@ struct IOBase {
       : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC),
         ring(ring_), my_tile(-1), wait_status(0) {}
 
-  // forcing tile of `day` resident?  On a tile change the thread first leaves its old tile (once).
-  __device__ __forceinline__ bool forcing_ready(int day) {
-    const int q = day / FORC_TILE;
-    if (q != my_tile) {
-      if (my_tile >= 0 && my_tile == q - 1) {
-        const int slot = my_tile % FORC_SLOTS;
-        const unsigned before = atomicAdd(&ring->left[slot], 1u);
-        if (before + 1 == ring->n_consumers) {            // last one out refills the slot
-          ring->left[slot] = 0;
-          const int next = my_tile + FORC_SLOTS;
-          if (next * FORC_TILE < a.D) tma_load_tile(ring, slot, a.forcing, next, a.D);
-        }
-        my_tile = -2 - q;                                   // left the old tile, not yet inside tile q
-      }
-      if (!mbar_test_parity(&ring->full[q % FORC_SLOTS], (unsigned)(q / FORC_SLOTS) & 1u)) return false;
-      my_tile = q;
-    }
-    return true;
-  }
-
-  // Warp-granular variant for the quad kernel (all lanes call it with the same `day`; the ring's consumers
-  // are the warps of the block and lane 0 does the bookkeeping).
+  // forcing tile of `day` resident?  Warp-granular: all lanes call it with the same `day`; the ring's consumers are
+  // the warps of the block and lane 0 does the bookkeeping (on a tile change the warp first leaves its old tile, once).
   __device__ __forceinline__ bool forcing_ready_warp(int day) {
     const int q = day / FORC_TILE;
     if (q != my_tile) {
       if (my_tile >= 0 && my_tile == q - 1) {
         __syncwarp();                                         // every lane is done reading the old tile
         if ((threadIdx.x & 31) == 0) {
-          const int slot = my_tile % FORC_SLOTS;
+          const int slot = (my_tile - ring->first_tile) % FORC_SLOTS;
           const unsigned before = atomicAdd(&ring->left[slot], 1u);
           if (before + 1 == ring->n_consumers) {
             ring->left[slot] = 0;
             const int next = my_tile + FORC_SLOTS;
-            if (next * FORC_TILE < a.D) tma_load_tile(ring, slot, a.forcing, next, a.D);
+            if (next * FORC_TILE < ring->end_day) tma_load_tile(ring, slot, a.forcing, next, a.D);
           }
         }
         my_tile = -2 - q;
       }
-      if (!mbar_test_parity(&ring->full[q % FORC_SLOTS], (unsigned)(q / FORC_SLOTS) & 1u)) return false;
+      const int rel = q - ring->first_tile;
+      if (!mbar_test_parity(&ring->full[rel % FORC_SLOTS], (unsigned)(rel / FORC_SLOTS) & 1u)) return false;
       my_tile = q;
     }
     return true;
@@ -243,34 +231,15 @@ struct IOBase {
     if (!ok) wait_status |= 4;
   }
 
-  // Routing wavefront: day `d` of this reach may start once every directly-upstream reach of the same
-  // member has published day `d` (acquire load pairs with the release store in publish()).
-  __device__ __forceinline__ bool ready(int day) {
-    if (!forcing_ready(day)) return false;
-    if (a.progress == nullptr) return true;
-    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
-    for (int e = e0; e < e1; ++e) {
-      const int* flag = a.progress + (size_t)m * a.S + a.parent_ids[e];
-      int done;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(flag) : "memory");
-      if (done <= day) return false;
-    }
-    return true;
-  }
+  // release store that pairs with the acquire load in upstream_ready()
   __device__ __forceinline__ void publish(int day) const {
     if (a.progress == nullptr) return;
     int* flag = a.progress + (size_t)m * a.S + s;
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(day + 1) : "memory");
   }
 
-  __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy) const {
-    const double* f = &ring->tiles[(day / FORC_TILE) % FORC_SLOTS][(day % FORC_TILE) * SIMPLYP_NF];
-    P = f[0];
-    E = f[1];
-    doy = f[2];
-  }
   __device__ __forceinline__ void forcing(int day, double& P, double& E, double& doy, double& T_air) const {
-    const double* f = &ring->tiles[(day / FORC_TILE) % FORC_SLOTS][(day % FORC_TILE) * SIMPLYP_NF];
+    const double* f = &ring->tiles[(day / FORC_TILE - ring->first_tile) % FORC_SLOTS][(day % FORC_TILE) * SIMPLYP_NF];
     P = f[0];
     E = f[1];
     doy = f[2];
@@ -297,7 +266,6 @@ struct RunIO : IOBase {
       us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
     }
   }
-  __device__ __forceinline__ bool wants_vr() const { return true; }
   __device__ __forceinline__ void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
                                        const double (&non)[13], const Cold&) const {
     double* row = a.out + (((size_t)m * a.S + s) * a.D + day) * SIMPLYP_NOUT;
@@ -348,7 +316,6 @@ struct CalIO : IOBase {
       us[3] += __ldcg(row + 3);
     }
   }
-  __device__ __forceinline__ bool wants_vr() const { return false; }
   __device__ __forceinline__ void emit(int day, const double (&)[NL], double, const double (&acc)[NA],
                                        const double (&)[13], const Cold& c) const {
     if (a.flux != nullptr) {
@@ -428,69 +395,6 @@ struct CalIO : IOBase {
   }
 };
 
-// ------------------------------------------------------------------------------------------ K1
-template <bool CAL>
-__global__ void __launch_bounds__(128, 2) simplyp_integrate_kernel(const KArgs a) {
-  extern __shared__ __align__(16) double smem_cold[];
-  // Networks: blocks take a ticket so that "lower index" means "dispatched earlier"; a reach only ever
-  // waits for reaches of lower topological level, which sit at lower indices, so a waiting block can only
-  // wait for blocks that are already running or finished (no deadlock even if the grid is not co-resident).
-  __shared__ unsigned s_vblock;
-  unsigned vblock = blockIdx.x;
-  if (a.ticket != nullptr) {
-    if (threadIdx.x == 0) s_vblock = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
-    __syncthreads();
-    vblock = s_vblock;
-  }
-  const long long idx = (long long)vblock * blockDim.x + threadIdx.x;
-  const long long n_items = (long long)a.n_work * a.M;
-
-  // forcing ring: thread 0 initialises the mbarriers and starts the first FORC_SLOTS tile copies
-  ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)blockDim.x * (sizeof(Cold) / sizeof(double)));
-  if (threadIdx.x == 0) {
-    const long long first = (long long)vblock * blockDim.x;
-    const long long rest = n_items - first;
-    ring->n_consumers = (unsigned)(rest < (long long)blockDim.x ? (rest > 0 ? rest : 0) : blockDim.x);
-    for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < FORC_SLOTS; ++i)
-      if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
-  }
-  __syncthreads();
-  if (idx >= n_items) return;
-  const int w = (int)(idx / a.M);
-  const int m = (int)(idx - (long long)w * a.M);
-  const int s = a.work_sc ? a.work_sc[w] : w;
-
-  Cold& c = *reinterpret_cast<Cold*>(smem_cold + (size_t)threadIdx.x * (sizeof(Cold) / sizeof(double)));
-  const double* mp = a.member_params + (size_t)m * SIMPLYP_NP_MEMBER;
-  const double* scp = a.sc_params + (size_t)(a.Msc > 1 ? m : 0) * a.S * SIMPLYP_NP_SC;
-  const double* sp = scp + (size_t)s * SIMPLYP_NP_SC;
-  const double A_qr0 = scp[(size_t)a.sc_qr0 * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-  // NC type of the last sub-catchment in run order (the reference's leaked loop variable)
-  const double* spl = scp + (size_t)(a.S - 1) * SIMPLYP_NP_SC;
-  const double fNCA_last = spl[SIMPLYP_SC_F_AR] * spl[SIMPLYP_SC_F_NC_AR] + spl[SIMPLYP_SC_F_NC_IG] * spl[SIMPLYP_SC_F_IG];
-  const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
-
-  ThreadCounters cnt;
-  RegStages ks;
-  if (CAL) {
-    CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP]);
-    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, ks, cnt);
-    io.finalise();
-  } else {
-    RunIO io(a, m, s, ring);
-    run_member_sc(mp, sp, A_qr0, nc_last, a.topt, a.D, c, io, ks, cnt);
-  }
-  if (a.diag) {
-    long long* dg = a.diag + ((size_t)m * a.S + s) * SIMPLYP_NDIAG;
-    dg[SIMPLYP_DG_STEPS] = cnt.steps;
-    dg[SIMPLYP_DG_REJECTED] = cnt.rejected;
-    dg[SIMPLYP_DG_RHS] = cnt.rhs_evals;
-    dg[SIMPLYP_DG_STATUS] = cnt.status;
-  }
-}
-
 // ------------------------------------------------------------------------------------------ K1 (quad form)
 // One QUAD of lanes per (member, sub-catchment) item, 8 items per warp in day lock-step (simplyp_quad.cuh).
 // Shared memory: one QuadMem per quad, then the forcing ring.
@@ -553,14 +457,26 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   QuadMem* qmem = reinterpret_cast<QuadMem*>(smem_cold);
   ForcingRing* ring = reinterpret_cast<ForcingRing*>(smem_cold + (size_t)quads_per_block * (sizeof(QuadMem) / sizeof(double)));
   for (;;) {                                       // one pass per virtual block of a claimed list (else one pass)
+    // Networks: the item count (levels padded to whole warps) is known on the device only (stiff_group_kernel); the
+    // grid is sized from a host-side upper bound, so trailing warps — and whole blocks — may have nothing to do.
+    // They leave before the forcing ring counts them as consumers (a warp is either all in range or all out of it).
+    int n_warps = blockDim.x >> 5;
+    if (a.level_item_off != nullptr) {
+      const long long rest = a.level_item_off[a.n_levels] - (long long)vblock * quads_per_block;
+      if (rest <= 0) return;
+      if (rest < (long long)quads_per_block) n_warps = (int)((rest + 7) >> 3);
+    }
     if (threadIdx.x == 0) {
-      ring->n_consumers = blockDim.x >> 5;          // the warps of the block
+      ring->n_consumers = (unsigned)n_warps;        // the warps of the block that integrate something
+      ring->first_tile = a.day_begin / FORC_TILE;
+      ring->end_day = a.day_end;
       for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       for (int i = 0; i < FORC_SLOTS; ++i)
-        if (i * FORC_TILE < a.D) tma_load_tile(ring, i, a.forcing, i, a.D);
+        if ((ring->first_tile + i) * FORC_TILE < a.day_end) tma_load_tile(ring, i, a.forcing, ring->first_tile + i, a.D);
     }
     __syncthreads();
+    if ((int)(threadIdx.x >> 5) >= n_warps) return;  // (network launches have no further block-wide barrier)
 
     long long idx = (long long)vblock * quads_per_block + (threadIdx.x >> 2);
     bool valid;
@@ -571,7 +487,6 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
       w = 0;
       m = a.perm ? a.perm[idx] : (int)idx;
     } else {
-      if (idx >= a.n_items_padded) idx = a.n_items_padded - 1;
       int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -705,7 +620,7 @@ __global__ void obs_rank_kernel(const double* obs, int D, double* obs_rank, doub
 
 // One block per (member, series): the simulated values of the observed days are compacted into shared memory
 // together with the observation ranks, ranked by counting (ties share the mean rank) and correlated.
-// Dynamic shared memory: 2 * cap doubles; a series longer than `cap` gets NaN.
+// Dynamic shared memory: 2 * cap doubles, cap >= D (longer records: spearman_long_kernel).
 __global__ void spearman_kernel(const double* sim_obs, const double* obs_rank, const double* obs_const, int V, int D,
                                 int cap, double* stats) {
   extern __shared__ double sh[];
@@ -772,6 +687,56 @@ __global__ void spearman_kernel(const double* sim_obs, const double* obs_rank, c
     const double cyy = rerank_obs ? red[0][0] : obs_const[8 * v + OC_SS_RANK];
     *out = cxy / sqrt(cxx * cyy);
   }
+}
+
+// The same for series too long for shared memory (more than ~12,800 days, i.e. 35 years of daily observations): no
+// compaction; every thread ranks its days by counting over the whole series in global memory (L1/L2 resident:
+// 16 B per day).  O(n D) reads per (member, series) — slower, but rare and exact.
+__global__ void spearman_long_kernel(const double* sim_obs, const double* obs_rank, const double* obs_const, int V, int D,
+                                     double* stats) {
+  __shared__ double red[3][128];
+  __shared__ int s_cnt[128];
+  const int mv = blockIdx.x, v = mv % V;
+  const double* sim = sim_obs + (size_t)mv * D;
+  const double* rk = obs_rank + (size_t)v * D;
+  int cnt = 0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) cnt += (rk[d] == rk[d]) && (sim[d] == sim[d]);
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) s_cnt[threadIdx.x] += s_cnt[threadIdx.x + k];
+    __syncthreads();
+  }
+  const int n = s_cnt[0];
+  double* out = stats + (size_t)mv * SIMPLYP_NSTAT + SIMPLYP_ST_SPEARMAN;
+  if (n < 2) { if (threadIdx.x == 0) *out = NAN; return; }
+  const bool rerank_obs = (double)n != obs_const[8 * v + OC_N];     // see spearman_kernel
+  const double mean_rank = 0.5 * (n + 1.0);
+  double sxy = 0.0, sxx = 0.0, syy = 0.0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const double x = sim[i];
+    double ro = rk[i];
+    if (!(x == x) || !(ro == ro)) continue;
+    int less = 0, equal = 0, l2 = 0, e2 = 0;
+    for (int j = 0; j < D; ++j) {
+      const double y = sim[j], r = rk[j];
+      const bool ok = (y == y) && (r == r);
+      less += ok && (y < x); equal += ok && (y == x);
+      if (rerank_obs) { l2 += ok && (r < ro); e2 += ok && (r == ro); }
+    }
+    const double rs = less + 0.5 * (equal + 1);
+    if (rerank_obs) ro = l2 + 0.5 * (e2 + 1);
+    sxy += (rs - mean_rank) * (ro - mean_rank);
+    sxx += (rs - mean_rank) * (rs - mean_rank);
+    syy += (ro - mean_rank) * (ro - mean_rank);
+  }
+  red[0][threadIdx.x] = sxy; red[1][threadIdx.x] = sxx; red[2][threadIdx.x] = syy;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) for (int j = 0; j < 3; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0][0] / sqrt(red[1][0] * (rerank_obs ? red[2][0] : obs_const[8 * v + OC_SS_RANK]));
 }
 
 // ------------------------------------------------------------------------------------------ waterbody sums
@@ -990,16 +955,22 @@ int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<in
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t off_po, off_pid, off_order, off_lvl_items, off_lvl_order, off_oc, off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket,
-      off_progress, off_flux, off_obs_log, off_obs_rank, off_sim_obs, total;
+  size_t off_po, off_pid, off_bylevel, off_lvlstart, off_topo_end, off_order, off_area, off_lvl_items, off_lvl_order, off_oc,
+      off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket, off_progress, off_flux, off_obs_log,
+      off_obs_rank, off_sim_obs, total;
 };
 
 WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = false) {
   WsLayout L;
   size_t o = 0;
+  // [off_po, off_topo_end): the host-built topology tables, filled by ONE copy from a pinned staging image
   L.off_po = o;    o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));
   L.off_pid = o;   o = align_up(o + sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
+  L.off_bylevel = o;  o = align_up(o + sizeof(int) * (size_t)d.n_sc);            // reaches sorted by (level, run order)
+  L.off_lvlstart = o; o = align_up(o + sizeof(int) * ((size_t)d.n_sc + 1));      // [n_levels+1] offsets into it
+  L.off_topo_end = o;
   L.off_order = o; o = align_up(o + sizeof(int) * (size_t)d.n_sc);
+  L.off_area = o;  o = align_up(o + sizeof(double) * (size_t)d.n_sc);            // area upstream of (and including) a reach
   L.off_lvl_items = o; o = align_up(o + sizeof(long long) * (2 * (size_t)d.n_sc + 1));   // <= 2 groups per level
   L.off_lvl_order = o; o = align_up(o + sizeof(int) * (2 * (size_t)d.n_sc + 1));
   L.off_oc = o;    o = align_up(o + sizeof(double) * 8 * (size_t)(d.n_obs_series > 0 ? d.n_obs_series : 1));
@@ -1026,6 +997,29 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   return L;
 }
 
+// Pinned host images of the topology tables of earlier calls.  The *_device entry points copy the caller's CSR
+// arrays (pageable host memory the caller may free or change right after the call) into such an image and enqueue
+// ONE asynchronous copy from it, so that they never synchronise and can be captured into a CUDA graph (a replay
+// reads the image again: images are kept until simplyp_release_cache()).  A call whose tables equal an earlier
+// image reuses it — and then allocates nothing, which stream capture in its strict mode requires.
+struct TopoImage { uint64_t hash; size_t bytes; char* host; };
+std::mutex g_topo_mutex;
+std::vector<TopoImage> g_topo_images;
+
+int topo_image_get(const std::vector<char>& img, const char** out) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < img.size(); ++i) { h ^= (unsigned char)img[i]; h *= 1099511628211ull; }
+  std::lock_guard<std::mutex> lock(g_topo_mutex);
+  for (const TopoImage& t : g_topo_images)
+    if (t.hash == h && t.bytes == img.size() && memcmp(t.host, img.data(), img.size()) == 0) { *out = t.host; return SIMPLYP_OK; }
+  char* host = nullptr;
+  SP_CUDA(cudaMallocHost(&host, img.size()));
+  memcpy(host, img.data(), img.size());
+  g_topo_images.push_back({h, img.size(), host});
+  *out = host;
+  return SIMPLYP_OK;
+}
+
 int check_common(const SimplypDims* dims, const SimplypOptions* opt, const void* forcing, const void* mp,
                  const void* scp, const int32_t* po) {
   if (!dims || !opt || !forcing || !mp || !scp || !po) return fail(SIMPLYP_EINVAL, "null argument%s");
@@ -1035,10 +1029,8 @@ int check_common(const SimplypDims* dims, const SimplypOptions* opt, const void*
   if (opt->sc_qr0 < 0 || opt->sc_qr0 >= dims->n_sc) return fail(SIMPLYP_EINVAL, "sc_qr0 out of range%s");
   if (!(opt->rtol > 0.0) || !(opt->atol >= 0.0) || !(opt->step_len > 0.0))
     return fail(SIMPLYP_EINVAL, "rtol/atol/step_len must be positive%s");
-  if (opt->lanes_per_item != 0 && opt->lanes_per_item != 1 && opt->lanes_per_item != 4)
-    return fail(SIMPLYP_EINVAL, "lanes_per_item must be 0 (default), 1 or 4%s");
-  if (opt->snow_on_device && opt->lanes_per_item == 1)
-    return fail(SIMPLYP_EINVAL, "snow_on_device needs the quad kernel (lanes_per_item 0 or 4)%s");
+  if (opt->lanes_per_item != 0 && opt->lanes_per_item != 4)
+    return fail(SIMPLYP_EINVAL, "lanes_per_item must be 0 (default) or 4: the one-thread-per-item kernel was retired%s");
   return SIMPLYP_OK;
 }
 
@@ -1050,14 +1042,6 @@ ThreadOptions make_topt(const SimplypOptions& o) {
   t.run_mode_cal = o.run_mode_cal; t.strict_quirks = o.strict_quirks;
   t.snow_on_device = o.snow_on_device;
   return t;
-}
-
-int pick_block(long long n_threads, int requested) {
-  if (requested > 0) return requested > 128 ? 128 : (requested < 32 ? 32 : (requested / 32) * 32);
-  // 4 warps per block land on the 4 sub-partitions of an SM (measured: 32- and 64-thread blocks stack
-  // their warps on the same sub-partitions and run 20 % slower at 10^4 members)
-  (void)n_threads;
-  return 128;
 }
 
 // Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.
@@ -1131,6 +1115,62 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   return SIMPLYP_OK;
 }
 
+// Orders the reaches of every topological level for the network launch: the reaches that are expected to be stiff
+// first, then the rest, so that the lock-step warps of a level hold either Rosenbrock items or explicit ones and do not
+// execute both attempts per iteration.  The expectation is an estimate from the FIRST parameter set: reach rate
+// constant at a nominal runoff of 3 mm/d over the whole upstream area (a_Q 86400/L (3 A_upstream/A_own)^b_Q / (1-b_Q),
+// model.py:127-130) against the kernel's switching rate.  It only steers the grouping: the method itself is still
+// chosen per item and day in the integration kernel.  One block; runs on the device because the parameters live
+// there and the *_device entry points must not synchronise.
+//   by_level[S], lvl_start[n_levels+1] : reaches sorted by (level, run order), from the host
+//   order[S]                           : reaches in launch order (group by group)
+//   grp_order[2 n_levels + 1]          : offsets of the groups into order[]
+//   grp_items[2 n_levels + 1]          : cumulative item counts, every group padded to whole warps of 8 quads
+__global__ void stiff_group_kernel(int S, int n_levels, int M, const int* by_level, const int* lvl_start, const int* po,
+                                   const int* pid, const double* sc_params, const double* member_params, double* area_up,
+                                   int* order, int* grp_order, long long* grp_items) {
+  const double aQ = member_params[SIMPLYP_P_A_Q], bQ = member_params[SIMPLYP_P_B_Q];
+  for (int L = 0; L < n_levels; ++L) {                 // parents sit on lower levels
+    for (int k = lvl_start[L] + threadIdx.x; k < lvl_start[L + 1]; k += blockDim.x) {
+      const int s = by_level[k];
+      double a = sc_params[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+      for (int e = po[s]; e < po[s + 1]; ++e) a += area_up[pid[e]];
+      area_up[s] = a;
+    }
+    __syncthreads();
+  }
+  for (int L = threadIdx.x; L < n_levels; L += blockDim.x) {
+    const int k0 = lvl_start[L], k1 = lvl_start[L + 1];
+    int n_stiff = 0;
+    for (int pass = 0; pass < 2; ++pass) {             // stable partition: stiff reaches, then the others
+      int w = k0 + (pass ? n_stiff : 0);
+      for (int k = k0; k < k1; ++k) {
+        const int s = by_level[k];
+        const double* sp = sc_params + (size_t)s * SIMPLYP_NP_SC;
+        const double qr = 3.0 * area_up[s] / sp[SIMPLYP_SC_A_CATCH];
+        const double rate = aQ * 86400.0 / sp[SIMPLYP_SC_L_REACH] * pow(qr, bQ) / (1.0 - bQ);
+        const bool stiff = rate > SP_STIFF_RATE;
+        if (stiff == (pass == 0)) { order[w++] = s; if (pass == 0) ++n_stiff; }
+      }
+    }
+    grp_order[2 * L] = k0;
+    grp_order[2 * L + 1] = k0 + n_stiff;
+  }
+  if (threadIdx.x == 0) grp_order[2 * n_levels] = S;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    grp_items[0] = 0;
+    for (int g = 0; g < 2 * n_levels; ++g) {
+      const long long n_real = (long long)(grp_order[g + 1] - grp_order[g]) * M;
+      run += (n_real + 7) / 8 * 8;                     // an empty group takes no items
+      grp_items[g + 1] = run;
+    }
+  }
+}
+
+// Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.  Everything is
+// enqueued on `st`; nothing here waits for the device.
 template <bool CAL>
 int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, const int32_t* po_host,
                   const int32_t* pid_host, char* ws, cudaStream_t st) {
@@ -1140,110 +1180,80 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   if (nl < 0) return fail(SIMPLYP_EINVAL, "topology: parents must precede children in run order%s");
   const int E = po_host[S];
   const WsLayout L = ws_layout(dims, E, CAL);
-  // Items are laid out group by group; a group = one topological level, split (quad kernel) into the reaches that
-  // are expected to be stiff and the rest, so that the lock-step warps of a level hold either Rosenbrock items or
-  // explicit ones and do not execute both attempts per iteration.  The expectation is a host-side estimate from the
-  // first parameter set: reach rate constant at a nominal runoff of 3 mm/d over the whole upstream area
-  // (a_Q 86400/L (3 A_upstream/A_own)^b_Q / (1-b_Q), model.py:127-130) against the kernel's switching rate.  It
-  // only steers the grouping: the method itself is still chosen per item and day on the device.
-  std::vector<int> group(S, 0);
-  int n_groups = nl;
-  if (S > 1 && opt.lanes_per_item != 1) {
-    std::vector<double> scp((size_t)S * SIMPLYP_NP_SC), mp0(SIMPLYP_NP_MEMBER), area_up(S, 0.0);
-    SP_CUDA(cudaMemcpyAsync(scp.data(), a.sc_params, sizeof(double) * scp.size(), cudaMemcpyDeviceToHost, st));
-    SP_CUDA(cudaMemcpyAsync(mp0.data(), a.member_params, sizeof(double) * mp0.size(), cudaMemcpyDeviceToHost, st));
-    SP_CUDA(cudaStreamSynchronize(st));
-    const double aQ = mp0[SIMPLYP_P_A_Q], bQ = mp0[SIMPLYP_P_B_Q];
-    for (int s = 0; s < S; ++s) {
-      area_up[s] = scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-      for (int e = po_host[s]; e < po_host[s + 1]; ++e) area_up[s] += area_up[pid_host[e]];
-      const double qr = 3.0 * area_up[s] / scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-      const double rate = aQ * 86400.0 / scp[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_L_REACH] * pow(qr, bQ) / (1.0 - bQ);
-      group[s] = 2 * lvl[s] + ((rate > SP_STIFF_RATE) ? 0 : 1);
-    }
-    n_groups = 2 * nl;
-  } else {
-    for (int s = 0; s < S; ++s) group[s] = lvl[s];
-  }
-  std::vector<int> order;
-  order.reserve(S);
-  for (int g = 0; g < n_groups; ++g)
-    for (int s = 0; s < S; ++s) if (group[s] == g) order.push_back(s);
+  constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
+  const int block = 128, qpb = block / 4;
+  const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
+                      (CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
+  a.n_work = S;
 
-  if (S > 1 || E > 0) {
-    if (!ws) return fail(SIMPLYP_EINVAL, "workspace required for n_sc > 1%s");
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_po, po_host, sizeof(int) * (S + 1), cudaMemcpyHostToDevice, st));
-    if (E > 0) SP_CUDA(cudaMemcpyAsync(ws + L.off_pid, pid_host, sizeof(int) * E, cudaMemcpyHostToDevice, st));
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_order, order.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
-    // the host vectors above are pageable: the copies are staged before these calls return
-    a.parent_offsets = reinterpret_cast<const int*>(ws + L.off_po);
-    a.parent_ids = reinterpret_cast<const int*>(ws + L.off_pid);
-  } else {
+  if (S == 1 && E == 0) {                    // an ensemble of one sub-catchment: items are the members
     int* zp = nullptr;
     SP_CUDA(cudaGetSymbolAddress((void**)&zp, g_zero_offsets));
     a.parent_offsets = zp;   // {0, 0}: no parents
     a.parent_ids = zp;
-  }
-  if (CAL) a.flux = (S > 1) ? reinterpret_cast<double*>(ws + L.off_flux) : nullptr;
-
-  // One launch for the whole network: threads are laid out level by level (all members of a reach are
-  // consecutive, so a warp holds one reach for 32 members whenever M >= 32) and advance as a wavefront.
-  a.n_work = S;
-  if (S > 1) {
-    a.work_sc = reinterpret_cast<const int*>(ws + L.off_order);
-    a.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
-    a.progress = reinterpret_cast<int*>(ws + L.off_progress);
-    SP_CUDA(cudaMemsetAsync(ws + L.off_ticket, 0, L.off_flux - L.off_ticket, st));
-  } else {
-    a.work_sc = nullptr;
-    a.ticket = nullptr;
-    a.progress = nullptr;
-  }
-  const long long n_items = (long long)S * dims.n_members;
-  long long n_items_padded = ((long long)dims.n_members + 7) / 8 * 8;
-  if (S > 1 && opt.lanes_per_item != 1) {
-    std::vector<long long> lvl_items(n_groups + 1, 0);
-    std::vector<int> lvl_order(n_groups + 1, 0);
-    for (int s = 0; s < S; ++s) lvl_order[group[s] + 1] += 1;
-    for (int g = 0; g < n_groups; ++g) {
-      const long long n_real = (long long)lvl_order[g + 1] * dims.n_members;
-      lvl_order[g + 1] += lvl_order[g];
-      lvl_items[g + 1] = lvl_items[g] + (n_real + 7) / 8 * 8;       // an empty group takes no items
-    }
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_items, lvl_items.data(), sizeof(long long) * (n_groups + 1), cudaMemcpyHostToDevice, st));
-    SP_CUDA(cudaMemcpyAsync(ws + L.off_lvl_order, lvl_order.data(), sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, st));
-    a.level_item_off = reinterpret_cast<const long long*>(ws + L.off_lvl_items);
-    a.level_order_off = reinterpret_cast<const int*>(ws + L.off_lvl_order);
-    a.n_levels = n_groups;
-    n_items_padded = lvl_items[n_groups];
-  }
-  a.n_items_padded = n_items_padded;
-  if (opt.lanes_per_item == 1) {
-    const int block = pick_block(n_items, opt.threads_per_block);
-    const long long grid = (n_items + block - 1) / block;
-    const size_t smem = (size_t)block * sizeof(Cold) + sizeof(ForcingRing);
-    simplyp_integrate_kernel<CAL><<<(unsigned)grid, block, smem, st>>>(a);
-  } else {
-    const int block = 128;
-    const int qpb = block / 4;
-    const long long grid = (n_items_padded + qpb - 1) / qpb;
-    const size_t smem = (size_t)qpb * sizeof(QuadMem) + sizeof(ForcingRing) +
-                        (CAL ? (size_t)qpb * STAT_STRIDE * sizeof(double) : 0);
-    constexpr int MODE = CAL ? MODE_CAL : MODE_RUN;
+    const long long grid = (((long long)dims.n_members + 7) / 8 * 8 + qpb - 1) / qpb;
     const int rc = order_members_by_cost<MODE>(dims, opt, a, L, ws, st);
     if (rc) return rc;
-    // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of
-    // the 2-blocks-per-SM variant
-    if (S > 1) simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
-    else if (quad_minblocks(grid) == 2) {
+    const int minb = quad_minblocks(grid);
+    if (minb == 2) {
       // planned placement: one block per list (n_sm first-lists, n_p + q second-lists), all resident at once
       const unsigned g = a.plan ? (unsigned)a.shape.n_lists() : (unsigned)grid;
       simplyp_quad_kernel<MODE, 2, false><<<g, block, smem, st>>>(a);
     }
-    else if (quad_minblocks(grid) == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);
+    else if (minb == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);
     else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    SP_CUDA(cudaGetLastError());
+    return SIMPLYP_OK;
   }
-  g_launches.fetch_add(1);
+
+  // ---- a network: topology tables -> workspace (one copy from a pinned image), grouping on the device
+  if (!ws) return fail(SIMPLYP_EINVAL, "workspace required for n_sc > 1%s");
+  std::vector<char> img(L.off_topo_end - L.off_po, 0);
+  int* i_po = reinterpret_cast<int*>(img.data() + (L.off_po - L.off_po));
+  int* i_pid = reinterpret_cast<int*>(img.data() + (L.off_pid - L.off_po));
+  int* i_byl = reinterpret_cast<int*>(img.data() + (L.off_bylevel - L.off_po));
+  int* i_ls = reinterpret_cast<int*>(img.data() + (L.off_lvlstart - L.off_po));
+  memcpy(i_po, po_host, sizeof(int) * (S + 1));
+  if (E > 0) memcpy(i_pid, pid_host, sizeof(int) * E);
+  for (int s = 0; s < S; ++s) i_ls[lvl[s] + 1] += 1;
+  for (int l = 0; l < nl; ++l) i_ls[l + 1] += i_ls[l];
+  {
+    std::vector<int> fill(i_ls, i_ls + nl);
+    for (int s = 0; s < S; ++s) i_byl[fill[lvl[s]]++] = s;
+  }
+  const char* pinned = nullptr;
+  int rc = topo_image_get(img, &pinned);
+  if (rc) return rc;
+  SP_CUDA(cudaMemcpyAsync(ws + L.off_po, pinned, img.size(), cudaMemcpyHostToDevice, st));
+  a.parent_offsets = reinterpret_cast<const int*>(ws + L.off_po);
+  a.parent_ids = reinterpret_cast<const int*>(ws + L.off_pid);
+  if (CAL) a.flux = reinterpret_cast<double*>(ws + L.off_flux);
+  a.work_sc = reinterpret_cast<const int*>(ws + L.off_order);
+  a.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
+  a.progress = reinterpret_cast<int*>(ws + L.off_progress);
+  SP_CUDA(cudaMemsetAsync(ws + L.off_ticket, 0, L.off_flux - L.off_ticket, st));
+  a.level_item_off = reinterpret_cast<const long long*>(ws + L.off_lvl_items);
+  a.level_order_off = reinterpret_cast<const int*>(ws + L.off_lvl_order);
+  a.n_levels = 2 * nl;
+  stiff_group_kernel<<<1, 1024, 0, st>>>(S, nl, dims.n_members, reinterpret_cast<const int*>(ws + L.off_bylevel),
+                                         reinterpret_cast<const int*>(ws + L.off_lvlstart), a.parent_offsets, a.parent_ids,
+                                         a.sc_params, a.member_params, reinterpret_cast<double*>(ws + L.off_area),
+                                         reinterpret_cast<int*>(ws + L.off_order), reinterpret_cast<int*>(ws + L.off_lvl_order),
+                                         reinterpret_cast<long long*>(ws + L.off_lvl_items));
+  // The padded item count depends on the split of each level, which only the device knows: the grid is sized for the
+  // worst split (a level of n reaches x M members pads to at most ceil8(n M) + 8 items when cut in two); blocks and
+  // warps beyond the actual count return at once.
+  long long bound = 0;
+  for (int l = 0; l < nl; ++l) {
+    const long long n = (long long)(i_ls[l + 1] - i_ls[l]) * dims.n_members;
+    bound += (n + 7) / 8 * 8 + ((dims.n_members % 8 != 0 && i_ls[l + 1] - i_ls[l] > 1) ? 8 : 0);
+  }
+  const long long grid = (bound + qpb - 1) / qpb;
+  // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of the
+  // 2-blocks-per-SM variant
+  simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
+  g_launches.fetch_add(2);
   SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;
 }
@@ -1261,37 +1271,41 @@ KArgs base_args(const SimplypDims& dims, const SimplypOptions& opt, const double
   return a;
 }
 
-// cached device buffers of the _host entry points
+// Cached device buffers of the _host entry points: one cache (buffers + stream + lock) PER DEVICE, so that host
+// threads driving different devices never touch each other's buffers; two threads on the same device take turns.
+constexpr int MAX_DEVICES = 64;
 struct HostCache {
-  int device = -1;
+  std::mutex lock;
   void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t stream = nullptr;
-} g_cache;
+};
+HostCache g_cache[MAX_DEVICES];
 
-int cache_get(int slot, size_t bytes, void** out) {
+int cache_get(HostCache& c, int slot, size_t bytes, void** out) {
   if (bytes == 0) bytes = 8;
-  if (g_cache.cap[slot] < bytes) {
-    if (g_cache.buf[slot]) cudaFree(g_cache.buf[slot]);
-    g_cache.buf[slot] = nullptr;
-    g_cache.cap[slot] = 0;
-    SP_CUDA(cudaMalloc(&g_cache.buf[slot], bytes));
-    g_cache.cap[slot] = bytes;
+  if (c.cap[slot] < bytes) {
+    if (c.buf[slot]) cudaFree(c.buf[slot]);
+    c.buf[slot] = nullptr;
+    c.cap[slot] = 0;
+    SP_CUDA(cudaMalloc(&c.buf[slot], bytes));
+    c.cap[slot] = bytes;
   }
-  *out = g_cache.buf[slot];
+  *out = c.buf[slot];
   return SIMPLYP_OK;
 }
 
-int cache_select_device(int device) {
+// Makes `device` current for the calling thread and readies its cache; the caller holds c.lock.
+int cache_select_device(int device, HostCache& c) {
+  SP_CUDA(cudaSetDevice(device));
+  if (!c.stream) SP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  return SIMPLYP_OK;
+}
+
+int check_device_index(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
-  if (device < 0 || device >= n) return fail(SIMPLYP_EINVAL, "device index out of range%s");
-  if (g_cache.device != device) {
-    simplyp_release_cache();
-    g_cache.device = device;
-  }
-  SP_CUDA(cudaSetDevice(device));
-  if (!g_cache.stream) SP_CUDA(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+  if (device < 0 || device >= n || device >= MAX_DEVICES) return fail(SIMPLYP_EINVAL, "device index out of range%s");
   return SIMPLYP_OK;
 }
 
@@ -1396,15 +1410,20 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
   rc = launch_levels<true>(*dims, *opt, a, parent_offsets, parent_ids, ws, st);
   if (rc) return rc;
   if (ranks) {
-    // shared memory: sim values + obs ranks of one series; at most one entry per day
-    int cap = dims->n_days;
+    // shared memory: sim values + obs ranks of one series, at most one entry per day; longer records take the
+    // global-memory variant
     const int cap_max = (200 * 1024) / 16;
-    if (cap > cap_max) cap = cap_max;
-    const size_t smem = (size_t)cap * 2 * sizeof(double);
-    if (smem > 48 * 1024)
-      SP_CUDA(cudaFuncSetAttribute(spearman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spearman_kernel<<<(unsigned)((size_t)dims->n_members * V), 128, smem, st>>>(
-        a.sim_obs, obs_rank, a.obs_const, V, dims->n_days, cap, stats);
+    if (dims->n_days <= cap_max) {
+      const int cap = dims->n_days;
+      const size_t smem = (size_t)cap * 2 * sizeof(double);
+      if (smem > 48 * 1024)
+        SP_CUDA(cudaFuncSetAttribute(spearman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spearman_kernel<<<(unsigned)((size_t)dims->n_members * V), 128, smem, st>>>(
+          a.sim_obs, obs_rank, a.obs_const, V, dims->n_days, cap, stats);
+    } else {
+      spearman_long_kernel<<<(unsigned)((size_t)dims->n_members * V), 128, 0, st>>>(
+          a.sim_obs, obs_rank, a.obs_const, V, dims->n_days, stats);
+    }
     g_launches.fetch_add(1);
     SP_CUDA(cudaGetLastError());
   }
@@ -1417,9 +1436,13 @@ int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* 
   int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
   if (rc) return rc;
   if (!out) return fail(SIMPLYP_EINVAL, "null output%s");
-  rc = cache_select_device(device);
+  rc = check_device_index(device);
   if (rc) return rc;
-  cudaStream_t st = g_cache.stream;
+  HostCache& hc = g_cache[device];
+  std::lock_guard<std::mutex> guard(hc.lock);
+  rc = cache_select_device(device, hc);
+  if (rc) return rc;
+  cudaStream_t st = hc.stream;
   const size_t M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
   const size_t b_forc = sizeof(double) * SIMPLYP_NF * D, b_mp = sizeof(double) * SIMPLYP_NP_MEMBER * M;
   const size_t b_sc = sizeof(double) * SIMPLYP_NP_SC * Msc * S, b_out = sizeof(double) * SIMPLYP_NOUT * M * S * D;
@@ -1428,8 +1451,8 @@ int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* 
   d2.reserved[0] = parent_offsets[S];
   const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, 0);
   void *d_forc, *d_mp, *d_sc, *d_out, *d_diag, *d_ws;
-  if ((rc = cache_get(0, b_forc, &d_forc)) || (rc = cache_get(1, b_mp, &d_mp)) || (rc = cache_get(2, b_sc, &d_sc)) ||
-      (rc = cache_get(3, b_out, &d_out)) || (rc = cache_get(4, b_diag, &d_diag)) || (rc = cache_get(5, b_ws, &d_ws)))
+  if ((rc = cache_get(hc, 0, b_forc, &d_forc)) || (rc = cache_get(hc, 1, b_mp, &d_mp)) || (rc = cache_get(hc, 2, b_sc, &d_sc)) ||
+      (rc = cache_get(hc, 3, b_out, &d_out)) || (rc = cache_get(hc, 4, b_diag, &d_diag)) || (rc = cache_get(hc, 5, b_ws, &d_ws)))
     return rc;
   SP_CUDA(cudaMemcpyAsync(d_forc, forcing, b_forc, cudaMemcpyHostToDevice, st));
   SP_CUDA(cudaMemcpyAsync(d_mp, member_params, b_mp, cudaMemcpyHostToDevice, st));
@@ -1451,9 +1474,13 @@ int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOpt
   if (rc) return rc;
   if (dims->n_obs_series <= 0 || !obs || !obs_desc || !stats)
     return fail(SIMPLYP_EINVAL, "observations and statistics buffers required%s");
-  rc = cache_select_device(device);
+  rc = check_device_index(device);
   if (rc) return rc;
-  cudaStream_t st = g_cache.stream;
+  HostCache& hc = g_cache[device];
+  std::lock_guard<std::mutex> guard(hc.lock);
+  rc = cache_select_device(device, hc);
+  if (rc) return rc;
+  cudaStream_t st = hc.stream;
   const size_t M = dims->n_members, S = dims->n_sc, D = dims->n_days, Msc = dims->n_sc_param_sets;
   const size_t V = dims->n_obs_series;
   const size_t b_forc = sizeof(double) * SIMPLYP_NF * D, b_mp = sizeof(double) * SIMPLYP_NP_MEMBER * M;
@@ -1464,9 +1491,9 @@ int simplyp_calibrate_host(int device, const SimplypDims* dims, const SimplypOpt
   d2.reserved[0] = parent_offsets[S];
   const size_t b_ws = (size_t)simplyp_workspace_bytes(&d2, opt->rank_stats ? 3 : 1);
   void *d_forc, *d_mp, *d_sc, *d_obs, *d_desc, *d_stats, *d_diag, *d_ws;
-  if ((rc = cache_get(0, b_forc, &d_forc)) || (rc = cache_get(1, b_mp, &d_mp)) || (rc = cache_get(2, b_sc, &d_sc)) ||
-      (rc = cache_get(3, b_stats, &d_stats)) || (rc = cache_get(4, b_diag, &d_diag)) ||
-      (rc = cache_get(5, b_ws, &d_ws)) || (rc = cache_get(6, b_obs, &d_obs)) || (rc = cache_get(7, b_desc, &d_desc)))
+  if ((rc = cache_get(hc, 0, b_forc, &d_forc)) || (rc = cache_get(hc, 1, b_mp, &d_mp)) || (rc = cache_get(hc, 2, b_sc, &d_sc)) ||
+      (rc = cache_get(hc, 3, b_stats, &d_stats)) || (rc = cache_get(hc, 4, b_diag, &d_diag)) ||
+      (rc = cache_get(hc, 5, b_ws, &d_ws)) || (rc = cache_get(hc, 6, b_obs, &d_obs)) || (rc = cache_get(hc, 7, b_desc, &d_desc)))
     return rc;
   SP_CUDA(cudaMemcpyAsync(d_forc, forcing, b_forc, cudaMemcpyHostToDevice, st));
   SP_CUDA(cudaMemcpyAsync(d_mp, member_params, b_mp, cudaMemcpyHostToDevice, st));
@@ -1517,14 +1544,26 @@ int simplyp_thornthwaite_pet_device(int32_t n_days, int32_t n_months, const doub
 }
 
 void simplyp_release_cache(void) {
-  for (int i = 0; i < 8; ++i) {
-    if (g_cache.buf[i]) cudaFree(g_cache.buf[i]);
-    g_cache.buf[i] = nullptr;
-    g_cache.cap[i] = 0;
+  int n = 0, prev = -1;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    HostCache& c = g_cache[d];
+    std::lock_guard<std::mutex> guard(c.lock);
+    if (!c.stream && !c.buf[0]) continue;
+    if (d < n) cudaSetDevice(d);
+    for (int i = 0; i < 8; ++i) {
+      if (c.buf[i]) cudaFree(c.buf[i]);
+      c.buf[i] = nullptr;
+      c.cap[i] = 0;
+    }
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
   }
-  if (g_cache.stream) cudaStreamDestroy(g_cache.stream);
-  g_cache.stream = nullptr;
-  g_cache.device = -1;
+  if (prev >= 0) cudaSetDevice(prev);
+  std::lock_guard<std::mutex> lock(g_topo_mutex);
+  for (TopoImage& t : g_topo_images) cudaFreeHost(t.host);
+  g_topo_images.clear();
 }
 
 int64_t simplyp_launch_count(void) { return g_launches.load(); }

@@ -35,7 +35,7 @@
 //   QuadHost4 (tests/hostemu only): T = V4, the 4 lanes are the 4 elements of a struct
 #pragma once
 
-#include "simplyp_thread.cuh"
+#include "simplyp_core.cuh"
 
 #ifndef SP_DAYSTART_FAC
 #define SP_DAYSTART_FAC 0.2   // day-start step = this x yesterday's last step (the forcing jumps at midnight);
@@ -437,7 +437,6 @@ struct QuadCarry {
 //   void wait(int day);                          // block until forcing and upstream inputs of `day` exist
 //   void forcing(int day, double& P, double& E, double& doy, double& T_air);
 //   void upstream(int day, double (&us)[4]);
-//   bool wants_vr();
 //   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
 //             const Cold& c);                    // called on the quad leader only
 //   void publish(int day);                       // leader only

@@ -82,10 +82,11 @@ class Engine:
     # ------------------------------------------------------------------ fused statistics
     def calibrate(self, forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc, opt,
                   stats=None, diag=None, max_workspace_bytes=None):
-        """Returns (stats [M][V][8], diag [M][S][4]); asynchronous on the current stream.
+        """Returns (stats [M][V][10], diag [M][S][4]); asynchronous on the current stream.
 
-        For networks (S > 1) the per-member flux exchange buffer is M*S*D*32 bytes; members are processed
-        in chunks that keep it under ``max_workspace_bytes`` (default: half of the free HBM).
+        The workspace grows with the members: M*S*D*32 bytes of flux exchange for networks (S > 1) and M*V*D*8
+        bytes of simulated values with ``opt.rank_stats``; members are processed in chunks that keep it under
+        ``max_workspace_bytes`` (default: half of the free HBM).
         """
         torch = _torch()
         D, M, Msc, S, sc_params = self._shapes(forcing, member_params, sc_params)
@@ -96,10 +97,10 @@ class Engine:
         if diag is None:
             diag = torch.zeros((M, S, pk.NDIAG), dtype=torch.int64, device=self.device)
         chunk = M
-        if S > 1:
+        per_member = (32 * S * D if S > 1 else 0) + (8 * V * D if opt.rank_stats else 0)
+        if per_member > 0:
             budget = max_workspace_bytes if max_workspace_bytes is not None else self.free_bytes() // 2
-            per_member = 32 * S * D + (8 * V * D if opt.rank_stats else 0)
-            chunk = max(1, min(M, int(budget // max(per_member, 1))))
+            chunk = max(1, min(M, int(budget // per_member)))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             for m0 in range(0, M, chunk):

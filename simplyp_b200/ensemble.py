@@ -92,7 +92,7 @@ def shard_bounds(n_members, world_size, rank):
 
 
 def all_gather_stats(local_stats, n_members, group=None):
-    """All-gather the per-member statistics [M_local][V][8] of every rank into [M][V][8] (rank order).
+    """All-gather the per-member statistics [M_local][V][10] of every rank into [M][V][10] (rank order).
 
     Uses ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).  Blocks are padded to the largest
     shard so one ``all_gather_into_tensor`` suffices.
@@ -123,7 +123,7 @@ def calibrate_ensemble(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, ob
     (reference ``inputs.py:159-210``) runs per member on the device, so ``D_snow_0`` and ``f_DDSM`` may be sampled.
     ``rank_stats``: also reduce Spearman's r (the whole table of ``goodness_of_fit_stats``).
 
-    Returns ``(stats [M][V][8] torch tensor on the device, labels [(reach, variable)], diag)``.
+    Returns ``(stats [M][V][10] torch tensor on the device, labels [(reach, variable)], diag)``.
     """
     import torch
     import torch.distributed as dist

@@ -26,11 +26,8 @@ DEFAULT_ATOL = 1e-10
 
 
 def make_options(p_SU, p, dynamic_options, topology, step_len=1.0, rtol=None, atol=None,
-                 strict_reference_quirks=True, threads_per_block=0, lanes_per_item=None):
-    """SimplypOptions for a run.  `lanes_per_item`: 4 = quad kernel (library default), 1 = one thread per
-    (member, sub-catchment); the environment variable SIMPLYP_LANES overrides the default for A/B runs."""
-    if lanes_per_item is None:
-        lanes_per_item = int(os.environ.get("SIMPLYP_LANES", "0"))
+                 strict_reference_quirks=True):
+    """SimplypOptions for a run (tolerances, dynamic options, run mode, the reach that sets the initial flow)."""
     sc_ids = topology.sc_ids
     qr0 = int(p["SC_Qr0"])
     if qr0 not in sc_ids:
@@ -44,8 +41,6 @@ def make_options(p_SU, p, dynamic_options, topology, step_len=1.0, rtol=None, at
         run_mode_cal=1 if p_SU["run_mode"] == "cal" else 0,
         sc_qr0=sc_ids.index(qr0),
         strict_quirks=1 if strict_reference_quirks else 0,
-        threads_per_block=int(threads_per_block),
-        lanes_per_item=int(lanes_per_item),
     )
 
 

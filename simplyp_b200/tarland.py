@@ -1,9 +1,10 @@
-"""The Tarland (Scotland) example set-up, rebuilt from the committed fixtures in ``tests/golden/``.
+"""The Tarland (Scotland) example set-up, rebuilt from the package data in ``simplyp_b200/data/tarland/``.
 
 The reference ships this set-up as an Excel workbook, a met CSV and two observation workbooks
 (``Example_Data/Tarland_Scotland``).  Those files are not available where the GPU tests and the
-benchmark run, so ``tests/golden/make_golden.py`` stores their contents as small JSON/npz fixtures and
-this module turns them back into exactly the pandas objects ``read_input_data`` returns.
+benchmark run, so ``tests/golden/make_golden.py`` stores their contents as small JSON/npz files (the example
+data of this package) and this module turns them back into exactly the pandas objects ``read_input_data``
+returns.
 """
 from __future__ import annotations
 
@@ -15,15 +16,15 @@ import pandas as pd
 
 from .inputs import snow_hydrol_inputs
 
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tarland")
 
 
 def _nan(x):
     return np.nan if x is None else x
 
 
-def load_parameters(golden_dir=GOLDEN_DIR):
-    with open(os.path.join(golden_dir, "tarland_inputs.json")) as f:
+def load_parameters(data_dir=DATA_DIR):
+    with open(os.path.join(data_dir, "tarland_inputs.json")) as f:
         d = json.load(f)
     p_SU = pd.Series({k: _nan(v) for k, v in d["p_SU"].items()}, name="Value", dtype=object)
     p_SU["n_SC"] = int(p_SU["n_SC"])
@@ -41,8 +42,8 @@ def load_parameters(golden_dir=GOLDEN_DIR):
 
 
 def load_met(st_dt="2004-01-01", end_dt="2004-12-31", D_snow_0=0.0, f_DDSM=2.74, inc_snowmelt=True,
-             golden_dir=GOLDEN_DIR):
-    z = np.load(os.path.join(golden_dir, "tarland_met.npz"))
+             data_dir=DATA_DIR):
+    z = np.load(os.path.join(data_dir, "tarland_met.npz"))
     idx = pd.date_range(str(z["day0"]), periods=int(z["n"]), freq="D", name="Date")
     met = pd.DataFrame({"T_air": z["T_air"], "PET": z["PET"], "Precipitation": z["Precipitation"]}, index=idx)
     met = met.truncate(before=st_dt, after=end_dt)
@@ -53,8 +54,8 @@ def load_met(st_dt="2004-01-01", end_dt="2004-12-31", D_snow_0=0.0, f_DDSM=2.74,
     return met
 
 
-def load_obs(st_dt="2004-01-01", end_dt="2004-12-31", golden_dir=GOLDEN_DIR):
-    z = np.load(os.path.join(golden_dir, "tarland_obs.npz"))
+def load_obs(st_dt="2004-01-01", end_dt="2004-12-31", data_dir=DATA_DIR):
+    z = np.load(os.path.join(data_dir, "tarland_obs.npz"))
     epoch = pd.Timestamp("1970-01-01")
     q = pd.DataFrame({"Q": z["Q"]}, index=pd.DatetimeIndex(epoch + pd.to_timedelta(z["q_days"], unit="D"), name="Date"))
     chem_cols = [c for c in ("SRP", "SS", "TDP", "TP", "PP") if c in z.files]

@@ -26,6 +26,7 @@ import pandas as pd
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+DATA = os.path.join(ROOT, "simplyp_b200", "data", "tarland")      # example data of the package (tarland.py)
 sys.path.insert(0, ROOT)
 
 from oracle import reference_live as rl          # noqa: E402
@@ -65,12 +66,12 @@ def main():
                  for c in p_SC.columns},
         "p_struc": {str(i): {"Upstream_SCs": None, "In_final_flux?": None} for i in p_struc.index},
     }
-    with open(os.path.join(HERE, "tarland_inputs.json"), "w") as f:
+    with open(os.path.join(DATA, "tarland_inputs.json"), "w") as f:
         json.dump(inputs, f, indent=1)
 
     met_all = pd.read_csv(os.path.join(REF, "Example_Data", "Tarland_Scotland", "Tarland_MetData_1981-2010.csv"),
                           parse_dates=True, dayfirst=True, index_col=0)
-    np.savez_compressed(os.path.join(HERE, "tarland_met.npz"),
+    np.savez_compressed(os.path.join(DATA, "tarland_met.npz"),
                         day0=str(met_all.index[0].date()), n=len(met_all),
                         T_air=met_all["T_air"].to_numpy(float), PET=met_all["PET"].to_numpy(float),
                         Precipitation=met_all["Precipitation"].to_numpy(float))
@@ -80,7 +81,7 @@ def main():
     q = _read_obs_workbook(os.path.join(obs_dir, "Coull_DailyMeanQ.xlsx"), None, None)[1]
     chem = _read_obs_workbook(os.path.join(obs_dir, "Coull_ChemObs.xlsx"), None, None)[1]
     epoch = pd.Timestamp("1970-01-01")
-    np.savez_compressed(os.path.join(HERE, "tarland_obs.npz"),
+    np.savez_compressed(os.path.join(DATA, "tarland_obs.npz"),
                         q_days=((q.index - epoch).days).to_numpy(), Q=q["Q"].to_numpy(float),
                         chem_days=((chem.index - epoch).days).to_numpy(),
                         **{c: chem[c].to_numpy(float) for c in chem.columns})

@@ -18,7 +18,7 @@ from oracle import reference_live as rl  # noqa: E402
 
 sp = rl.load()
 ri = sp.inputs
-z = np.load(os.path.join(HERE, "tarland_met.npz"), allow_pickle=True)
+z = np.load(os.path.join(HERE, "..", "..", "simplyp_b200", "data", "tarland", "tarland_met.npz"), allow_pickle=True)
 idx = pd.date_range("1981-01-01", periods=len(z["T_air"]), freq="D")
 t_air = pd.Series(z["T_air"].astype(float), index=idx)
 out = {"latitude_deg": 57.1, "years": {}}

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "hostemu.cpp")
 LIB = os.path.join(HERE, "libsimplyp_hostemu.so")
 DEPS = [SRC, os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_core.cuh"),
-        os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_thread.cuh"),
+        os.path.join(HERE, "scalar_program.h"),
         os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_quad.cuh"),
         os.path.join(ROOT, "simplyp_b200", "csrc", "simplyp_plan.cuh"),
         os.path.join(ROOT, "include", "simplyp_b200.h")]

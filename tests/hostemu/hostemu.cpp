@@ -1,4 +1,4 @@
-// TEST HARNESS ONLY — compiles simplyp_core.cuh / simplyp_thread.cuh for the host so that the
+// TEST HARNESS ONLY — compiles simplyp_core.cuh / simplyp_quad.cuh (and the scalar cross-check program, scalar_program.h) for the host so that the
 // CPU-only test tier (`pytest -m "not gpu"`) can exercise the same per-thread arithmetic and
 // control flow the CUDA kernels run, against the oracle, in a container without a GPU.
 // Nothing in simplyp_b200/ loads this library; the product has no CPU execution path.
@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../simplyp_b200/csrc/simplyp_thread.cuh"
+#include "scalar_program.h"
 #include "../../simplyp_b200/csrc/simplyp_quad.cuh"
 #include "../../simplyp_b200/csrc/simplyp_plan.cuh"
 

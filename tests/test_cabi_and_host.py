@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_cabi.EXPORTS) == declared
     lib2 = _cabi.load()
-    assert lib2.simplyp_abi_version() == 2
+    assert lib2.simplyp_abi_version() == 3
     assert b"sm_100a" in lib2.simplyp_version()
 
 
@@ -183,7 +183,7 @@ def test_read_input_data_roundtrip(tmp_path, golden_dir):
     import simplyp_b200 as sp
     from simplyp_b200 import tarland
     p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="n")
-    z = np.load(os.path.join(golden_dir, "tarland_met.npz"))
+    z = np.load(os.path.join(tarland.DATA_DIR, "tarland_met.npz"))
     idx = pd.date_range(str(z["day0"]), periods=int(z["n"]), freq="D")
     sel = (idx >= "2003-12-01") & (idx <= "2005-01-31")
     with open(tmp_path / "met.csv", "w") as f:

@@ -418,30 +418,16 @@ def test_stiff_reach_vs_oracle(cabi, area):
     assert per_day > 20
 
 
-def test_one_thread_per_item_kernel_still_agrees(cabi, golden_dir):
-    """The round-1 kernel (lanes_per_item = 1), kept for A/B measurements: same parity bound on Tarland 2004, and
-    its fused statistics agree with the quad kernel's to the integration tolerance."""
-    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
-
-    def runner(forcing, member, sc, po, pid, opt):
-        opt.lanes_per_item = 1
-        return cabi.run_host(forcing, member, sc, po, pid, opt)
-
-    parity.check_tarland(runner, golden_dir, "y")
+def test_retired_scalar_kernel_is_refused(cabi):
+    """lanes_per_item = 1 (the round-1 one-thread-per-item kernel) is no longer on the product ABI."""
+    from simplyp_b200 import model as spm, packing as pk, tarland
     p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
     topo = pk.build_topology(p_struc, p["SC_list"])
-    samples = ens.latin_hypercube(96, seed=12)
-    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
-    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
-    forcing = pk.forcing_matrix(met)
-    st = {}
-    for lanes in (1, 4):
-        opt = spm.make_options(p_SU, p, dyn, topo, lanes_per_item=lanes)
-        st[lanes], dg = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
-        assert not np.any(dg[..., 3])
-    for col in (1, 2, 4, 5, 6):      # NSE, log NSE, r2, bias, nRMSD
-        assert np.allclose(st[1][..., col], st[4][..., col], rtol=2e-4, atol=2e-5), col
-    assert np.array_equal(st[1][..., 0], st[4][..., 0])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    opt.lanes_per_item = 1
+    with pytest.raises(cabi.SimplypError):
+        cabi.run_host(pk.forcing_matrix(met.iloc[:5]), pk.member_vector(p, p_LU)[None],
+                      pk.sc_matrix(p_SC, topo.sc_ids)[None], topo.parent_offsets, topo.parent_ids, opt)
 
 
 def test_against_the_reference_shipped_csvs(cabi, golden_dir):
@@ -459,8 +445,8 @@ def test_thornthwaite_pet_on_device(cabi, golden_dir):
     import json
     import pandas as pd
     import simplyp_b200 as sp
-    from simplyp_b200 import inputs
-    z = np.load(os.path.join(golden_dir, "tarland_met.npz"), allow_pickle=True)
+    from simplyp_b200 import inputs, tarland
+    z = np.load(os.path.join(tarland.DATA_DIR, "tarland_met.npz"), allow_pickle=True)
     idx = pd.date_range("1981-01-01", periods=len(z["T_air"]), freq="D")
     met = pd.DataFrame({"T_air": z["T_air"].astype(float), "PET": z["PET"].astype(float)}, index=idx)
     want = sp.daily_PET(57.1, met)
@@ -566,3 +552,122 @@ def test_planned_placement_is_invisible_in_the_results(cabi, M, monkeypatch):
         assert np.array_equal(runs["0"][0], runs["1"][0]) and np.array_equal(runs["0"][1], runs["1"][1])
         assert np.array_equal(runs["no pilot"][0], runs["1"][0]) and np.array_equal(runs["no pilot"][1], runs["1"][1])
         assert np.isfinite(runs["1"][0]).all()
+
+
+def test_device_entry_points_capture_into_a_cuda_graph(cabi):
+    """include/simplyp_b200.h: the *_device entry points enqueue on the caller's stream WITHOUT synchronising — also
+    for networks, whose stiff/non-stiff grouping of the reaches is now made on the device.  Proof: a full-output run
+    and a calibration run of a 5-reach network are captured into CUDA graphs (a synchronising call would abort the
+    capture) and the replays give the bits of the direct calls."""
+    import torch
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from simplyp_b200.engine import Engine
+    from tests.golden.networks import network5_inputs
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    p, p_LU, p_SC, p_struc = network5_inputs(p, p_LU, p_SC, p_struc)
+    pk.validate_land_use(p_SC, p["SC_list"])
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(37, seed=4)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    met = met.iloc[:150]
+    obs_m, desc, labels = pk.obs_arrays({5: obs[1]}, topo, met.index, ("Q", "TDP"))
+    eng = Engine(0)
+    d_f, d_m, d_s = eng.to_device(pk.forcing_matrix(met)), eng.to_device(member), eng.to_device(sc)
+    d_o, d_d = eng.to_device(obs_m), eng.to_device(desc)
+    po, pid = topo.parent_offsets, topo.parent_ids
+    out_ref, diag_ref = eng.run(d_f, d_m, d_s, po, pid, opt)                 # direct calls (also the warm-up: the
+    st_ref, _ = eng.calibrate(d_f, d_m, d_s, po, pid, d_o, d_d, opt)         # topology image and workspace exist now)
+    torch.cuda.synchronize()
+    out_ref, diag_ref, st_ref = out_ref.clone(), diag_ref.clone(), st_ref.clone()
+    out_g, diag_g = torch.zeros_like(out_ref), torch.zeros_like(diag_ref)
+    st_g = torch.zeros_like(st_ref)
+    dg2 = torch.zeros_like(diag_ref)
+    g_run, g_cal = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_run):
+        eng.run(d_f, d_m, d_s, po, pid, opt, out=out_g, diag=diag_g)
+    with torch.cuda.graph(g_cal):
+        eng.calibrate(d_f, d_m, d_s, po, pid, d_o, d_d, opt, stats=st_g, diag=dg2)
+    for _ in range(2):
+        out_g.zero_(); diag_g.zero_(); st_g.zero_()
+        g_run.replay()
+        g_cal.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out_g, out_ref) and torch.equal(diag_g, diag_ref)
+        assert torch.equal(st_g.nan_to_num(nan=-7.0), st_ref.nan_to_num(nan=-7.0))
+    assert int(diag_ref[..., 3].max().item()) == 0
+
+
+def test_host_entry_points_from_concurrent_threads(cabi):
+    """The *_host entry points keep one buffer cache per device behind a per-device lock: host threads that drive
+    different devices (or, on a one-GPU box, the same device) get the results of the single-threaded calls while
+    their ensembles — of different sizes, so the caches are re-allocated under each other's feet — interleave."""
+    import threading
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(dynamic="y")
+    met = met.iloc[:60]
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    forcing = pk.forcing_matrix(met)
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
+    n_dev = cabi.load().simplyp_device_count()
+    jobs = []
+    for t, M in enumerate((300, 1100, 64, 700)):
+        samples = ens.latin_hypercube(M, seed=40 + t)
+        member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+        jobs.append((member, sc, t % n_dev))
+    want = [(cabi.run_host(forcing, m, s, topo.parent_offsets, topo.parent_ids, opt, device=d)[0],
+             cabi.calibrate_host(forcing, m, s, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt, device=d)[0])
+            for m, s, d in jobs]
+    got, errors = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            m, s, d = jobs[i]
+            for _ in range(3):
+                out, _dg = cabi.run_host(forcing, m, s, topo.parent_offsets, topo.parent_ids, opt, device=d)
+                st, _dg = cabi.calibrate_host(forcing, m, s, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt, device=d)
+            got[i] = (out, st)
+        except Exception as e:       # noqa: BLE001 - surfaced below
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for i in range(len(jobs)):
+        assert np.array_equal(got[i][0], want[i][0]), i
+        assert np.array_equal(got[i][1], want[i][1], equal_nan=True), i
+
+
+def test_spearman_of_a_record_longer_than_shared_memory(cabi):
+    """Spearman's r for series of more than 12,800 observed days (round 1 returned NaN there): 14,000 days of
+    synthetic daily observations; the device value against the host table (pandas ranks, pinned to the reference)."""
+    from simplyp_b200 import ensemble as ens, inputs as spi, model as spm, packing as pk, stats as sps, synthetic, tarland
+    p_SU, dyn, p, p_LU, p_SC, p_struc, met0, obs0 = tarland.load(dynamic="y")
+    met = spi.snow_hydrol_inputs(p["D_snow_0"], p["f_DDSM"], synthetic.synthetic_met(14000, seed=5))
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(3, seed=8)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    out, dg = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+    assert not np.any(dg[..., 3])
+    rng = np.random.default_rng(0)
+    q0 = out[0, 0, :, 5] * float(sc[0, 0, pk.SC_INDEX["A_catch"]]) * 1000 / 86400
+    q_obs = np.round(q0 * np.exp(rng.normal(0, 0.3, len(q0))), 3)          # rounded: ties in the observations
+    q_obs[rng.random(len(q0)) < 0.02] = np.nan
+    obs = {1: pd.DataFrame({"Q": q_obs}, index=met.index)}
+    obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q",))
+    assert np.isfinite(obs_m[0]).sum() > 12800
+    opt.rank_stats = 1
+    st, _ = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+    for i in range(3):
+        _tc, r = spm.raw_to_frames(out[i, 0], met.index, float(sc[i, 0, pk.SC_INDEX["A_catch"]]), p["Msoil_m2"],
+                                   float(member[i, pk.MEMBER_INDEX["f_TDP"]]), "None", None)
+        want = dict(zip(sps.STATS_COLUMNS, sps.gof_one(obs[1]["Q"], r["Q_cumecs"])))
+        # 2e-6 like the short-record test: the device forms Q_cumecs as Qr*A*(1000/86400), pandas as Qr*A*1000/86400;
+        # a last-bit difference can swap two neighbouring ranks out of 13,700
+        assert abs(st[i, 0, 8] - want["Spearmans r"]) <= 2e-6, (i, st[i, 0], want)     # SIMPLYP_ST_SPEARMAN = 8
