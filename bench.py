@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the SimplyP daily mass-balance integration path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--members M_PER_GPU] [--period 2004|full]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
+                    [--members M] [--period 2004|full]
 
-Workload (BASELINE.json configs[1]): the Tarland set-up (1 sub-catchment, shipped 2004 period, both
-dynamic options on), a Latin-hypercube ensemble of 10^4 parameter sets PER GPU, fused goodness-of-fit
-statistics (NSE, log-NSE, Gaussian log-likelihood, r2, bias, nRMSD) against observed Q and TDP.
-One "step" = one pass of the whole ensemble over the whole period.  Metric: member-sub-catchment-days
-per second, whole job.  Members are sharded over ranks with no data-path collective; the only
-collective is the all-gather of the per-member statistics (inside the timed step).
+One "step" = one pass of the whole workload over its whole period.  Metric (BASELINE.json): member-sub-catchment-days
+per second, whole job.  Workloads = BASELINE.json `configs`:
 
-Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is obtained.
+  --config 2 (default)  Tarland (1 sub-catchment, 2004, both dynamic options on), Latin-hypercube ensemble of 10^4
+                        parameter sets PER GPU (weak scaling), fused goodness-of-fit statistics vs observed Q and TDP,
+                        all-gather of the statistics inside the timed step; e2e = simplyp_calibrate_host.
+  --config 4            the same ensemble with 10^6 members IN TOTAL, sharded over the GPUs (strong scaling).
+  --config 3            synthetic 256-sub-catchment branching network, 30-year daily forcing, both dynamic options on,
+                        --members parameter sets per GPU (default 64), full daily output kept in HBM;
+                        e2e = simplyp_run_host on a member subset whose output fits pinned host memory.
+  --config 5            synthetic 4096-sub-catchment x 3 land-use network, 50-year daily run, full daily output written
+                        to HBM (200 B per member-SC-day), --members per GPU (default 4).
+
+Members are sharded over ranks with no data-path collective; the only collective is the all-gather of the per-member
+statistics (configs 2 and 4).  Prints ONE JSON line (rank 0).  See DESIGN.md §5 for how each field is obtained.
+`--impl reference` times the reference's own CPU algorithm (oracle port: per-day scipy odeint/LSODA at the reference's
+rtol=0.01) on all host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -28,6 +37,8 @@ sys.path.insert(0, ROOT)
 METRIC = "member-sub-catchment-days/sec"
 UNIT = "member-SC-days/s"
 F_RHS, F_STEP_EXTRA, F_DAY = 140.0, 700.0, 120.0      # SURVEY.md §8(d) algorithmic flop counts
+B_DAY = 200.0                                         # bytes written per member-SC-day (full output)
+FP64_DFMA_PER_SM_CLK = 64                             # B200: 64 DFMA per SM per clock (nominal)
 
 
 def parse_args():
@@ -36,23 +47,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--members", type=int, default=10000, help="ensemble members per GPU")
-    ap.add_argument("--period", default="2004", choices=["2004", "full"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--members", type=int, default=None,
+                    help="members per GPU (configs 2, 3, 5; defaults 10000 / 64 / 4) or in total (config 4; 10^6)")
+    ap.add_argument("--period", default="2004", choices=["2004", "full"], help="configs 2 and 4: Tarland period")
     ap.add_argument("--rtol", type=float, default=None)
     ap.add_argument("--atol", type=float, default=None)
     ap.add_argument("--pilot-days", type=int, default=0, help="cost pilot: 0 = library default, -1 = off")
+    ap.add_argument("--e2e-members", type=int, default=None,
+                    help="configs 3 and 5: members of the end-to-end leg (default: as many as fit 48 GB of pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target time of each cpu_baseline leg")
+    args = ap.parse_args()
+    if args.members is None:
+        args.members = {2: 10000, 3: 64, 4: 1000000, 5: 4}[args.config]
+    return args
 
 
 def period_dates(period):
     return ("2004-01-01", "2004-12-31") if period == "2004" else ("1981-01-01", "2010-12-31")
 
 
-# ------------------------------------------------------------------------------------------ workload
+# ------------------------------------------------------------------------------------------ workloads
 def build_workload(period, n_members, seed=20260101, member_offset=0):
-    """Arrays of the calibration call for `n_members` members (deterministic in the global member index)."""
+    """Configs 2/4: arrays of the calibration call for `n_members` members (deterministic in the member index)."""
     from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
     st, end = period_dates(period)
     p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load(st, end, dynamic="y")
@@ -63,6 +81,19 @@ def build_workload(period, n_members, seed=20260101, member_offset=0):
     return dict(p_SU=p_SU, dyn=dyn, p=p, p_LU=p_LU, p_SC=p_SC, p_struc=p_struc, met=met, obs=obs, topo=topo,
                 samples=samples, member=member, sc=sc, forcing=pk.forcing_matrix(met), obs_m=obs_m, desc=desc,
                 labels=labels)
+
+
+def workload_text(args, M_local, D, S):
+    if args.config in (2, 4):
+        how = ("%d-member LHS ensemble per GPU" % M_local) if args.config == 2 else \
+              ("%d-member LHS ensemble in total, sharded over the GPUs" % args.members)
+        return ("Tarland %s (D=%d days, S=1), %s, fused NSE/log-NSE/log-likelihood vs observed Q and TDP, "
+                "Dynamic_EPC0/erodibility on" % (args.period, D, how))
+    if args.config == 3:
+        return ("synthetic 256-sub-catchment branching reach network (seed 3), 30-year daily forcing (D=%d), all "
+                "dynamic options on, %d parameter sets per GPU, full daily output kept in HBM" % (D, M_local))
+    return ("synthetic 4096-sub-catchment x 3 land-use network (seed 3), 50-year daily run (D=%d), full daily output "
+            "written to HBM (200 B per member-SC-day), %d parameter sets per GPU" % (D, M_local))
 
 
 # ------------------------------------------------------------------------------------------ CPU legs (oracle port)
@@ -100,6 +131,63 @@ def cpu_port_throughput(period, members_per_core, cores, rtol, atol):
     return days / busy, days, busy, wall
 
 
+_NET = {}
+
+
+def cpu_network_throughput(cfg, n_days, processes, rtol, atol):
+    """Oracle port on the first `n_days` of a network configuration (all reaches, one parameter set): the reference's
+    SC-major loop nest, the reaches of a topological level spread over `processes` host processes
+    (oracle/parallel.py; bit-identical to the serial call).  Returns (SC-days/s, SC-days, seconds)."""
+    from oracle import parallel as opar, simplyp_oracle as orc
+    from simplyp_b200 import synthetic
+    if cfg not in _NET:
+        _NET[cfg] = synthetic.scale_config(cfg)
+    w = _NET[cfg]
+    met = w["met"].iloc[:n_days]
+    p, lu, sc, ups = orc.unpack_pandas(w["p_struc"], w["p_LU"], w["p_SC"], w["p"])
+    a = (met["P"].to_numpy(), met["PET"].to_numpy(), met.index.dayofyear.to_numpy(), p, lu, sc, ups)
+    kw = dict(run_mode="cal", dynamic_EPC0=True, dynamic_erodibility=True, rtol=rtol, atol=atol, mxstep=500000)
+    t0 = time.perf_counter()
+    if processes == 1:
+        orc.run_network(*a, **kw)
+    else:
+        opar.run_network_parallel(*a, processes=processes, **kw)
+    dt = time.perf_counter() - t0
+    units = len(sc) * n_days
+    return units / dt, units, dt
+
+
+def cpu_baseline_legs(args, rtol, atol, D):
+    """the reference's algorithm on the host cores — all cores and one process, at the GPU run's
+    tolerance and at the reference's own (rtol=0.01, model.py:640).  Bounded samples of the same workload."""
+    cores = os.cpu_count() or 1
+    legs = {}
+    if args.config in (2, 4):
+        per_core = 1 if args.period == "full" else max(1, int(round(args.cpu_seconds / 1.2)))
+        v, days, busy, _ = cpu_port_throughput(args.period, per_core, cores, rtol, atol)
+        legs["all"] = (v, "%d members x %d days (same LHS members), one member per task on %d processes (%.1f s)"
+                       % (per_core * cores, D, cores, busy))
+        v1, _, b1, _ = cpu_port_throughput(args.period, max(1, per_core // 2), 1, rtol, atol)
+        vr, _, br, _ = cpu_port_throughput(args.period, per_core, cores, 0.01, None)
+        vr1, _, br1, _ = cpu_port_throughput(args.period, max(1, per_core // 2), 1, 0.01, None)
+    else:
+        S = 256 if args.config == 3 else 4096
+        n_all = max(2, int(args.cpu_seconds * 350.0 * cores * 0.5 / S))     # ~350 SC-days/s/core at 1e-7, level-limited
+        v, units, dt = cpu_network_throughput(args.config, n_all, cores, rtol, atol)
+        legs["all"] = (v, "first %d days of the %d-reach network, one parameter set, reaches of a level on %d processes (%.1f s)"
+                       % (n_all, S, cores, dt))
+        n_one = max(1, int(args.cpu_seconds * 350.0 / S))
+        v1, _, b1 = cpu_network_throughput(args.config, n_one, 1, rtol, atol)
+        vr, _, br = cpu_network_throughput(args.config, n_all, cores, 0.01, None)
+        vr1, _, br1 = cpu_network_throughput(args.config, n_one, 1, 0.01, None)
+    return {"value": legs["all"][0], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port = per-day scipy odeint/LSODA with a Python RHS at the GPU run's rtol/atol; " + legs["all"][1],
+            "rtol": rtol, "atol": atol,
+            "single_process": {"value": v1, "cores": 1, "seconds": b1},
+            "reference_tolerance": {"rtol": 0.01, "atol": "odeint default", "value": vr, "cores": cores, "seconds": br,
+                                    "single_process": {"value": vr1, "cores": 1, "seconds": br1}}}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's own CPU algorithm (oracle port: per-day scipy odeint/LSODA at the
     reference's rtol=0.01 with a Python RHS callback) on all host cores.  The reference is pure Python and
@@ -108,34 +196,45 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    days_per_member = 366 if args.period == "2004" else 10957
-    per_core = 2 if args.period == "2004" else 1
-    n_days_eff = None
-    times = []
-    days = 0
-    for it in range(args.warmup + args.steps):
-        v, d, busy, wall = cpu_port_throughput(args.period, per_core, cores, 0.01, None)
-        if it >= args.warmup:
-            times.append(busy)
-            days = d
+    times, units = [], 0
+    if args.config in (2, 4):
+        D = 366 if args.period == "2004" else 10957
+        S = 1
+        per_core = 2 if args.period == "2004" else 1
+        sample = ("each step integrates a %d-member Latin-hypercube sample drawn by the same generator and seed, one member "
+                  "per task on %d processes (bounded sample; member-SC-days/s does not depend on the ensemble size on the CPU)"
+                  % (per_core * cores, cores))
+        extra = {"members_per_step": per_core * cores}
+        for it in range(args.warmup + args.steps):
+            v, d, busy, wall = cpu_port_throughput(args.period, per_core, cores, 0.01, None)
+            if it >= args.warmup:
+                times.append(busy)
+                units = d
+    else:
+        S, D = (256, 10958) if args.config == 3 else (4096, 18262)
+        n_days = max(2, int(2.0 * 1500.0 * cores * 0.5 / S))       # about 2 s per step
+        sample = ("each step integrates the first %d days of the %d-reach network for one parameter set, the reaches of a "
+                  "topological level spread over %d processes (bounded sample of the %d-day record)" % (n_days, S, cores, D))
+        extra = {"days_per_step": n_days}
+        for it in range(args.warmup + args.steps):
+            v, u, dt = cpu_network_throughput(args.config, n_days, cores, 0.01, None)
+            if it >= args.warmup:
+                times.append(dt)
+                units = u
     ms = 1e3 * float(np.mean(times))
-    value = days / (ms * 1e-3)
+    value = units / (ms * 1e-3)
+    cfg = {"workload": workload_text(args, args.members if args.config != 4 else args.members // max(args.gpus, 1), D, S),
+           "bench_config": args.config, "sample": sample, "days": D, "sub_catchments": S, "rtol": 0.01,
+           "atol": "odeint default (the reference's own solver settings, model.py:640)"}
+    cfg.update(extra)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "Tarland forcing/obs fixtures; "
-        "Latin-hypercube parameter sets (seed 20260101)",
-        "config": {"workload": "Tarland %s (D=%d days, S=1), %d-member LHS ensemble per GPU, fused NSE/log-NSE/"
-                               "log-likelihood vs observed Q and TDP, Dynamic_EPC0/erodibility on"
-                               % (args.period, days_per_member, args.members),
-                   "sample": "each step integrates a %d-member Latin-hypercube sample drawn by the same generator and seed "
-                             "(bounded sample; member-SC-days/s does not depend on the ensemble size on the CPU)"
-                             % (per_core * cores),
-                   "members_per_step": per_core * cores, "days": days_per_member, "sub_catchments": 1,
-                   "rtol": 0.01, "atol": "odeint default (the reference's own solver settings, model.py:640)"},
+        "scaling": "strong" if args.config == 4 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic: Tarland forcing/obs example data or seeded synthetic network; seeded parameter sets",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d members x %d days per step, one member per task on %d processes, "
-                                   "scipy odeint (LSODA) rtol=0.01 as the reference calls it" % (per_core * cores, days_per_member, cores)},
+                         "sample": sample + "; scipy odeint (LSODA) rtol=0.01 as the reference calls it"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -196,11 +295,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def _pinned(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from simplyp_b200 import _cabi, ensemble as ens, model as spm, packing as pk
+    from simplyp_b200 import _cabi, ensemble as ens, model as spm, packing as pk, synthetic
     from simplyp_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,31 +313,58 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    M_local = args.members
-    M_total = M_local * world
-    w = build_workload(args.period, M_total)
-    lo, hi = ens.shard_bounds(M_total, world, rank)
-    opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol)
-    opt.pilot_days = args.pilot_days
-    kernel_name = "simplyp_quad_kernel<cal>"
     eng = Engine(local_rank)
-    S, D, V = w["topo"].n_sc, w["forcing"].shape[0], w["obs_m"].shape[0]
+    calibration = args.config in (2, 4)
+
+    # ---- workload: this rank's member block [lo, hi) of M_total
+    if calibration:
+        M_total = args.members * world if args.config == 2 else args.members
+        w = build_workload(args.period, M_total)
+        opt = spm.make_options(w["p_SU"], w["p"], w["dyn"], w["topo"], 1.0, args.rtol, args.atol)
+        kernel_name = "simplyp_quad_kernel<cal>"
+        data = "Tarland forcing/obs example data (simplyp_b200/data/tarland); Latin-hypercube parameter sets, seed 20260101"
+    else:
+        M_total = args.members * world
+        w = synthetic.scale_config(args.config, M_total)
+        opt = w["opt"]
+        if args.rtol is not None:
+            opt.rtol = args.rtol
+        if args.atol is not None:
+            opt.atol = args.atol
+        kernel_name = "simplyp_quad_kernel<run,stiff>"
+        data = ("seeded synthetic network (simplyp_b200/synthetic.py: random_network seed 3, synthetic_met seed 11), Tarland "
+                "parameters, members differ in a_Q (0.8x..1.2x)")
+    opt.pilot_days = args.pilot_days
+    lo, hi = ens.shard_bounds(M_total, world, rank)
+    M_local = hi - lo
+    topo = w["topo"]
+    S, D = topo.n_sc, w["forcing"].shape[0]
+    po, pid = topo.parent_offsets, topo.parent_ids
+    sc_local = w["sc"][lo:hi] if w["sc"].shape[0] > 1 else w["sc"]
 
     # ---- device-resident leg ("value"): inputs already in HBM
     d_forc = eng.to_device(w["forcing"])
     d_mem = eng.to_device(w["member"][lo:hi])
-    d_sc = eng.to_device(w["sc"][lo:hi] if w["sc"].shape[0] > 1 else w["sc"])
-    d_obs = eng.to_device(w["obs_m"])
-    d_desc = eng.to_device(w["desc"])
-    stats = torch.empty((hi - lo, V, pk.NSTAT), dtype=torch.float64, device=eng.device)
-    diag = torch.zeros((hi - lo, S, pk.NDIAG), dtype=torch.int64, device=eng.device)
+    d_sc = eng.to_device(sc_local)
+    diag = torch.zeros((M_local, S, pk.NDIAG), dtype=torch.int64, device=eng.device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=eng.device)   # > 126 MB L2
-    po, pid = w["topo"].parent_offsets, w["topo"].parent_ids
+    if calibration:
+        V = w["obs_m"].shape[0]
+        d_obs = eng.to_device(w["obs_m"])
+        d_desc = eng.to_device(w["desc"])
+        # the kernel writes this rank's statistics straight into its slot of the pre-allocated gather buffer
+        gb = ens.GatherBuffers(M_total, (V, pk.NSTAT), eng.device)
+        stats = gb.local
 
-    def step():
-        st, _ = eng.calibrate(d_forc, d_mem, d_sc, po, pid, d_obs, d_desc, opt, stats=stats, diag=diag)
-        return ens.all_gather_stats(st, M_total) if world > 1 else st
+        def step():
+            eng.calibrate(d_forc, d_mem, d_sc, po, pid, d_obs, d_desc, opt, stats=stats, diag=diag)
+            return gb.gather()
+    else:
+        out = torch.empty((M_local, S, D, pk.NOUT), dtype=torch.float64, device=eng.device)
+
+        def step():
+            eng.run(d_forc, d_mem, d_sc, po, pid, opt, out=out, diag=diag)
+            return out
 
     def barrier():
         if world > 1:
@@ -241,10 +372,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # clocks are sampled from before the warm-up steps (nvidia-smi needs ~0.1 s to start and a timed region of 10
-    # steps lasts 0.15 s) to the end of the timed steps: every sample is taken under the bench load
+    # steps of config 2 lasts 0.15 s) to the end of the timed steps: every sample is taken under the bench load
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         flush.zero_()
         step()
     barrier()
@@ -253,11 +385,10 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    gathered = None
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the events)
         ev[k][0].record()
-        gathered = step()
+        step()
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -274,30 +405,72 @@ def run_ours(args):
     dg = diag.sum(dim=(0, 1)).cpu().numpy().astype(float)
     n_steps, n_rej, n_rhs = dg[0], dg[1], dg[2]
     status_any = int(diag[..., 3].max().item())
-    flops_local = n_rhs * F_RHS + n_steps * F_STEP_EXTRA + (hi - lo) * S * D * F_DAY
+    units_local = M_local * S * D
+    flops_local = n_rhs * F_RHS + n_steps * F_STEP_EXTRA + units_local * F_DAY
+    # work of the ACCEPTED attempts only (a rejected attempt is integrator overhead, not algorithmic work)
+    acc_frac = 1.0 - n_rej / max(n_steps, 1.0)
+    flops_accepted = (n_rhs * F_RHS + n_steps * F_STEP_EXTRA) * acc_frac + units_local * F_DAY
     kernel_ms = float(np.mean(step_ms))
-    achieved_tf = flops_local / (kernel_ms * 1e-3) / 1e12
     fp64_peak = _cabi.measure_fp64_peak(local_rank, 3) if rank == 0 else None
+    if calibration:
+        stats_ref = stats.clone()
+        alg_bytes = (d_forc.numel() + d_mem.numel() + d_sc.numel() + d_obs.numel()) * 8 + stats.numel() * 8 * 2
+    else:
+        alg_bytes = units_local * B_DAY + (d_forc.numel() + d_mem.numel() + d_sc.numel()) * 8
+        ref_rows = out[0, S - 1, :64].clone()         # the outlet's first days, to compare with the end-to-end leg
 
     # ---- end-to-end leg: host buffers through the C-ABI, H2D + D2H inside the timed region
-    h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in
-         (("forcing", w["forcing"]), ("member", w["member"][lo:hi]),
-          ("sc", w["sc"][lo:hi] if w["sc"].shape[0] > 1 else w["sc"]), ("obs", w["obs_m"]))}
-    h2d = sum(v.nbytes for v in h.values()) + w["desc"].nbytes
-    d2h = (hi - lo) * V * pk.NSTAT * 8 + (hi - lo) * S * pk.NDIAG * 8
+    if calibration:
+        M_e2e = M_local
+        h = {k: _pinned(v) for k, v in (("forcing", w["forcing"]), ("member", w["member"][lo:hi]), ("sc", sc_local),
+                                        ("obs", w["obs_m"]))}
+        st_host = _pinned(np.empty((M_e2e, V, pk.NSTAT)))
+        dg_host = _pinned(np.zeros((M_e2e, S, pk.NDIAG), dtype=np.int64))
+        h2d = sum(v.nbytes for v in h.values()) + w["desc"].nbytes
+        d2h = st_host.nbytes + dg_host.nbytes
+
+        def e2e_step():
+            _cabi.calibrate_host(h["forcing"], h["member"], h["sc"], po, pid, h["obs"], w["desc"], opt, device=local_rank,
+                                 stats=st_host, diag=dg_host)
+        api = "simplyp_calibrate_host (C-ABI, pinned host buffers)"
+        e2e_reps = args.steps
+    else:
+        del out
+        torch.cuda.empty_cache()
+        # as many members as fit a pinned host buffer of at most a quarter of the free host memory (48 GB at most)
+        per_member = S * D * pk.NOUT * 8
+        try:
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        except Exception:
+            avail = 64 << 30
+        fit = max(1, int(min(avail // 4, 48 << 30) // per_member))
+        M_e2e = min(M_local, args.e2e_members if args.e2e_members else fit)
+        h = {k: _pinned(v) for k, v in (("forcing", w["forcing"]), ("member", w["member"][lo:lo + M_e2e]),
+                                        ("sc", sc_local[:M_e2e] if sc_local.shape[0] > 1 else sc_local))}
+        out_host = torch.empty((M_e2e, S, D, pk.NOUT), dtype=torch.float64, pin_memory=True).numpy()
+        dg_host = _pinned(np.zeros((M_e2e, S, pk.NDIAG), dtype=np.int64))
+        h2d = sum(v.nbytes for v in h.values())
+        d2h = out_host.nbytes + dg_host.nbytes
+
+        def e2e_step():
+            _cabi.run_host(h["forcing"], h["member"], h["sc"], po, pid, opt, device=local_rank, out=out_host, diag=dg_host)
+        api = "simplyp_run_host (C-ABI, pinned host buffers; %d of the %d members per GPU)" % (M_e2e, M_local)
+        e2e_reps = max(2, min(args.steps, 3))
     for _ in range(2):
-        _cabi.calibrate_host(h["forcing"], h["member"], h["sc"], po, pid, h["obs"], w["desc"], opt, device=local_rank)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st_host, _dg = _cabi.calibrate_host(h["forcing"], h["member"], h["sc"], po, pid, h["obs"], w["desc"], opt,
-                                            device=local_rank)
+    for _ in range(e2e_reps):
+        e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = M_total * S * D * args.steps / float(e2e_s.item())
-    same = bool(np.array_equal(st_host, stats.cpu().numpy(), equal_nan=True))
+    e2e_value = M_e2e * world * S * D * e2e_reps / float(e2e_s.item())
+    if calibration:
+        same = bool(np.array_equal(st_host, stats_ref.cpu().numpy(), equal_nan=True))
+    else:
+        same = bool(np.array_equal(out_host[0, S - 1, :64], ref_rows.cpu().numpy()))
 
     if rank == 0:
         peaks = {}
@@ -309,52 +482,73 @@ def run_ours(args):
         traffic, traffic_src = None, None
         try:     # measured DRAM traffic of this kernel at this size, from the committed ncu capture (null if none)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ent = tj.get("%s|%d|%d" % (kernel_name, hi - lo, D))
+            ent = tj.get("%s|%d|%d|%d" % (kernel_name, M_local, S, D)) or tj.get("%s|%d|%d" % (kernel_name, M_local, D))
             if ent:
                 traffic, traffic_src = ent["bytes"], ent["source"]
         except Exception:
             pass
-        alg_bytes = (d_forc.numel() + d_mem.numel() + d_sc.numel() + d_obs.numel()) * 8 + stats.numel() * 8 * 2
+        achieved_tf = flops_accepted / (kernel_ms * 1e-3) / 1e12
+        achieved_tf_all = flops_local / (kernel_ms * 1e-3) / 1e12
+        achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp64_nominal = n_sm * FP64_DFMA_PER_SM_CLK * 2 * sm_mhz * 1e6 / 1e12
+        fp64 = {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (achieved_tf / fp64_peak) if fp64_peak else None,
+                "achieved_incl_rejected_attempts": achieved_tf_all,
+                "frac_incl_rejected_attempts": (achieved_tf_all / fp64_peak) if fp64_peak else None,
+                "peak_source": "simplyp_measure_fp64_peak (DFMA probe, this run); MEASURED_PEAKS.json has no FP64 figure",
+                "peak_nominal_at_clock": fp64_nominal,
+                "peak_nominal_note": "%d SMs x 64 DFMA/clk x 2 flop x %.0f MHz (median SM clock of this run)" % (n_sm, sm_mhz),
+                "algorithmic_flops_per_launch": flops_accepted,
+                "algorithmic_flops_per_launch_incl_rejected": flops_local,
+                "flops_per_member_sc_day": flops_accepted / units_local}
+        hbm = {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+               "algorithmic_bytes_per_launch": int(alg_bytes),
+               "bytes_per_member_sc_day": (B_DAY if not calibration else alg_bytes / units_local),
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+        primary = hbm if args.config == 5 else fp64
+        roofline = {"bound": "hbm" if args.config == 5 else "fp64"}
+        roofline.update({k: primary[k] for k in ("achieved", "peak", "unit", "frac")})
+        roofline.update({"traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": kernel_ms,
+                         "steps_per_member_sc_day": n_steps / units_local, "rejected_frac": n_rej / max(n_steps, 1.0),
+                         "rhs_per_member_sc_day": n_rhs / units_local, "fp64": fp64, "hbm": hbm})
+        if args.config == 5:
+            roofline["note"] = ("BASELINE.json names this the output-bandwidth-bound case; measured, the step is bound by the "
+                                "FP64/issue rate of the integration (fp64 sub-object): at 200 B per member-SC-day the HBM "
+                                "ceiling is %.2e member-SC-days/s, the FP64 ceiling at this workload's %.0f flop per "
+                                "member-SC-day is %.2e" % (hbm_peak * 1e9 / B_DAY, flops_accepted / units_local,
+                                                           (fp64_peak or fp64_nominal) * 1e12 / (flops_accepted / units_local)))
+        if calibration:
+            launches_text = ("pilot pass (days 0-7, member order) + counting sort (2) + observation constants + main pass "
+                             "(days 8-end, cost order, blocks placed by SM)" + (" + NCCL all-gather" if world > 1 else ""))
+        else:
+            launches_text = "stiff/non-stiff grouping of the reaches (1 block) + the network launch (routing wavefront inside)"
+        cfg = {"workload": workload_text(args, M_local, D, S), "bench_config": args.config,
+               "members_total": M_total, "members_per_gpu": M_local, "days": D, "sub_catchments": S,
+               "rtol": opt.rtol, "atol": opt.atol, "parallelism": "ensemble members sharded over %d GPU(s)" % world,
+               "l2": "256 MB buffer written between timed steps (outside the per-step CUDA events)"
+                     + ("" if calibration else "; the output written per step (%.1f GB) is far larger than L2" % (units_local * B_DAY / 1e9)),
+               "launches_per_step": launches_text}
+        if calibration:
+            cfg["obs_series"] = [list(l) for l in w["labels"]]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "Tarland forcing/obs fixtures (tests/golden); "
-            "Latin-hypercube parameter sets, seed 20260101",
-            "config": {"workload": "Tarland %s (D=%d days, S=1), %d-member LHS ensemble per GPU, fused NSE/log-NSE/"
-                                   "log-likelihood vs observed Q and TDP, Dynamic_EPC0/erodibility on" % (args.period, D, M_local),
-                       "members_total": M_total, "days": D, "sub_catchments": S, "obs_series": [list(l) for l in w["labels"]],
-                       "rtol": opt.rtol, "atol": opt.atol, "parallelism": "ensemble members sharded over %d GPU(s)" % world,
-                       "l2": "256 MB buffer written between timed steps (outside the per-step CUDA events)",
-                       "launches_per_step": "pilot pass (days 0-7, member order) + counting sort (2) + observation "
-                                            "constants + main pass (days 8-end, cost order, blocks placed by SM)"},
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.config == 4 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic: " + data,
+            "config": cfg,
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "simplyp_calibrate_host (C-ABI, pinned host buffers)", "matches_device_leg": same},
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / fp64_peak) if fp64_peak else None, "traffic": traffic,
-                         "traffic_source": traffic_src,
-                         "peak_source": "simplyp_measure_fp64_peak (DFMA probe, this run); MEASURED_PEAKS.json has no FP64 figure",
-                         "kernel": kernel_name, "kernel_ms": kernel_ms,
-                         "algorithmic_flops_per_launch": flops_local,
-                         "steps_per_member_day": n_steps / ((hi - lo) * S * D), "rejected_frac": n_rej / max(n_steps, 1.0),
-                         "rhs_per_member_day": n_rhs / ((hi - lo) * S * D),
-                         "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "algorithmic_bytes_per_launch": int(alg_bytes),
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+                    "api": api, "members_per_gpu": M_e2e, "steps": e2e_reps, "matches_device_leg": same},
+            "roofline": roofline,
             "clocks": clocks, "integrator_status_bits": status_any, "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            per_core = 1 if args.period == "full" else max(1, int(round(args.cpu_seconds / 1.2)))
             try:
-                v, days, busy, wall = cpu_port_throughput(args.period, per_core, cores, opt.rtol, opt.atol)
-                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": "%d members x %d days (same LHS members), oracle port = per-day scipy "
-                                                  "odeint/LSODA with a Python RHS at the GPU run's rtol/atol, one member "
-                                                  "per task on %d processes (%.1f s)" % (per_core * cores, D, cores, busy)}
+                line["cpu_baseline"] = cpu_baseline_legs(args, opt.rtol, opt.atol, D)
             except Exception as e:  # keep the bench line even if the CPU leg cannot run
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -243,7 +243,10 @@ int simplyp_sum_to_waterbody_device(const SimplypDims* dims, const double* out, 
 
 /* daily_PET (inputs.py:232-312; Thornthwaite 1948 via :416-508) on the device, for a record of whole calendar
  * years starting on 1 January: t_air[d * t_stride] daily mean air temperature, month_start[n_months + 1] = day index
- * at which each calendar month starts (device), year_is_leap[n_months / 12] (device), latitude in degrees;
+ * at which each calendar month starts (device), year_is_leap[n_months / 12] (device; bit 0 = leap year, bit 1 = the
+ * year uses the leap-year daylight-hours table: the reference keeps that table for all years after its first leap
+ * year, inputs.py:269-273 — pass 3 for a leap year and 2 for the later non-leap years to reproduce it, 0/3 per
+ * year for the calendar-correct choice), latitude in degrees;
  * pet[d * pet_stride] receives mm/day (stride 4 writes column 1 of a forcing matrix in place when pet = forcing + 1). */
 int simplyp_thornthwaite_pet_device(int32_t n_days, int32_t n_months, const double* t_air, int32_t t_stride,
                                     const int32_t* month_start, const int32_t* year_is_leap, double latitude_deg,

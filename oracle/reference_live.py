@@ -202,3 +202,49 @@ def goodness_of_fit_stats(p_SU, df_R_dict, obs_dict):
     sp = load()
     with contextlib.redirect_stdout(io.StringIO()):
         return sp.goodness_of_fit_stats(p_SU, df_R_dict, obs_dict)
+
+
+# --------------------------------------------------------------------------- daily_PET wrapper (inputs.py:232-312)
+class _PandasProxy(types.ModuleType):
+    """Stands in for the name ``pd`` inside the reference's ``inputs`` module: everything is pandas, except that
+    ``DatetimeIndex(freq=, start=, end=)`` — a constructor form pandas dropped in 1.0 — is answered by
+    ``pd.date_range`` (what that form always did)."""
+
+    def __getattr__(self, name):
+        return getattr(pd, name)
+
+    @staticmethod
+    def DatetimeIndex(*args, **kw):
+        if "start" in kw or "end" in kw:
+            kw.pop("dayfirst", None)
+            return pd.date_range(start=kw.pop("start", None), end=kw.pop("end", None), freq=kw.pop("freq", None), **kw)
+        return pd.DatetimeIndex(*args, **kw)
+
+
+@contextlib.contextmanager
+def _month_end_alias():
+    """``Series.resample('M')`` (month end; renamed 'ME' in pandas 2.2 and refused in 3) for the duration of a call."""
+    orig = pd.Series.resample
+
+    def resample(self, rule, *a, **k):
+        return orig(self, "ME" if rule == "M" else rule, *a, **k)
+
+    pd.Series.resample = resample
+    try:
+        yield
+    finally:
+        pd.Series.resample = orig
+
+
+def daily_PET(latitude, met_df):
+    """The reference's own ``daily_PET`` wrapper (``inputs.py:232-312``), unmodified, on a deep copy of ``met_df``.
+    Two more process-local shims let it run under pandas 3: the month-end alias and the ``DatetimeIndex`` form."""
+    sp = load()
+    mod = sp.inputs
+    saved = mod.pd
+    mod.pd = _PandasProxy("pandas_proxy")
+    try:
+        with _month_end_alias(), contextlib.redirect_stdout(io.StringIO()):
+            return mod.daily_PET(latitude, met_df.copy(deep=True))
+    finally:
+        mod.pd = saved

@@ -185,7 +185,7 @@ def snow_hydrol_inputs(D_snow_0, f_DDSM, precip, t_air):
 # --------------------------------------------------------------------------- driver  model.py:193-827
 def run_network(forcing_P, forcing_PET, doy, p, p_LU, p_SC, upstream, run_mode="cal",
                 dynamic_EPC0=False, dynamic_erodibility=False, step_len=1.0,
-                rtol=0.01, atol=None, mxstep=5000, strict_quirks=True, n_days=None):
+                rtol=0.01, atol=None, mxstep=5000, strict_quirks=True, n_days=None, only=None, preset=None):
     """Integrate a whole reach network, SC-major then day-minor like the reference.
 
     Plain-python inputs:
@@ -196,6 +196,10 @@ def run_network(forcing_P, forcing_PET, doy, p, p_LU, p_SC, upstream, run_mode="
       p_SC   : dict sc_id -> dict name -> value
       upstream : dict sc_id -> list of directly-upstream sc ids; iteration order of ``p_SC`` is the
                  run order and must be upstream-first (model.py:524 raises KeyError otherwise)
+
+    ``only`` / ``preset`` serve ``oracle/parallel.py`` (the same computation spread over processes): ``preset`` maps
+    sub-catchment ids to ``(ode [D][12], nonode [D][13])`` computed earlier, which are taken as they are, and only the
+    ids in ``only`` are integrated (their direct parents must be preset or in ``only``).
 
     Returns dict with ``ode`` [S][D][12], ``nonode`` [S][D][13], ``Kf`` {sc: Kf}, ``nfe`` total RHS calls,
     ``sc_ids``.
@@ -237,6 +241,11 @@ def run_network(forcing_P, forcing_PET, doy, p, p_LU, p_SC, upstream, run_mode="
     nst = 0
 
     for SC in sc_ids:
+        if preset is not None and SC in preset:
+            ode_out[pos[SC]], non_out[pos[SC]] = preset[SC]
+            continue
+        if only is not None and SC not in only:
+            continue
         q = p_SC[SC]
         f_A, f_NC_A, nc_type = der[SC]
         post_nc_type = last_nc_type if strict_quirks else nc_type         # :442,676 use the leaked name

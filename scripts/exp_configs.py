@@ -16,22 +16,7 @@ from simplyp_b200.engine import Engine
 
 
 def build(cfg, members=1):
-    p_SU, dyn, p, p_LU, p_SC0, p_struc0, met, obs = tarland.load(dynamic="y")
-    if cfg == 3:
-        n_sc, n_days, all_lu = 256, 10958, False
-    else:
-        n_sc, n_days, all_lu = 4096, 18262, True
-    p, p_SC, p_struc = synthetic.random_network(p, p_SC0[1], n_sc=n_sc, seed=3, all_land_uses=all_lu)
-    met = synthetic.synthetic_met(n_days, seed=11)
-    met = spi.snow_hydrol_inputs(p["D_snow_0"], p["f_DDSM"], met)
-    pk.validate_land_use(p_SC, p["SC_list"])
-    topo = pk.build_topology(p_struc, p["SC_list"])
-    opt = spm.make_options(p_SU, p, dyn, topo)
-    member = np.repeat(pk.member_vector(p, p_LU)[None], members, axis=0)
-    if members > 1:      # spread a_Q a little so that the members differ
-        member[:, pk.MEMBER_INDEX["a_Q"]] *= np.linspace(0.8, 1.2, members)
-    sc = pk.sc_matrix(p_SC, topo.sc_ids)[None]
-    return dict(topo=topo, opt=opt, member=member, sc=sc, forcing=pk.forcing_matrix(met), p_struc=p_struc)
+    return synthetic.scale_config(cfg, members)
 
 
 def main():

@@ -159,8 +159,19 @@ def topology_levels(parent_offsets, parent_ids):
 
 
 # ------------------------------------------------------------------------------------------ host-buffer calls
-def run_host(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, device=0, want_diag=True):
-    """numpy in / numpy out through ``simplyp_run_host``.  Returns (out [M][S][D][25], diag [M][S][4])."""
+def _result_buffer(given, shape, dtype):
+    """A caller-supplied result buffer (e.g. pinned host memory) must be C-contiguous with the expected shape/dtype."""
+    if given is None:
+        return np.zeros(shape, dtype=dtype) if dtype == np.int64 else np.empty(shape, dtype=dtype)
+    if tuple(given.shape) != tuple(shape) or given.dtype != dtype or not given.flags["C_CONTIGUOUS"]:
+        raise ValueError("result buffer must be a C-contiguous %s array of shape %s" % (np.dtype(dtype).name, tuple(shape)))
+    return given
+
+
+def run_host(forcing, member_params, sc_params, parent_offsets, parent_ids, opt, device=0, want_diag=True, out=None,
+             diag=None):
+    """numpy in / numpy out through ``simplyp_run_host``.  Returns (out [M][S][D][25], diag [M][S][4]); ``out`` /
+    ``diag`` may be given (pinned host memory makes the copies asynchronous DMA)."""
     lib = require_device()
     forcing = _c64(forcing)
     member_params = _c64(member_params)
@@ -171,8 +182,8 @@ def run_host(forcing, member_params, sc_params, parent_offsets, parent_ids, opt,
     Msc, S = sc_params.shape[0], sc_params.shape[1]
     po, pid = _topology_arrays(parent_offsets, parent_ids)
     dims = make_dims(M, S, D, Msc, 0, int(po[-1]))
-    out = np.empty((M, S, D, pk.NOUT), dtype=np.float64)
-    diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
+    out = _result_buffer(out, (M, S, D, pk.NOUT), np.float64)
+    diag = _result_buffer(diag, (M, S, pk.NDIAG), np.int64)
     rc = lib.simplyp_run_host(device, C.byref(dims), C.byref(opt), _dptr(forcing), _dptr(member_params),
                               _dptr(sc_params), _iptr(po), _iptr(pid), _dptr(out),
                               diag.ctypes.data_as(C.POINTER(C.c_int64)) if want_diag else None)
@@ -181,8 +192,8 @@ def run_host(forcing, member_params, sc_params, parent_offsets, parent_ids, opt,
 
 
 def calibrate_host(forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc, opt,
-                   device=0, want_diag=True):
-    """numpy in / numpy out through ``simplyp_calibrate_host``.  Returns (stats [M][V][8], diag)."""
+                   device=0, want_diag=True, stats=None, diag=None):
+    """numpy in / numpy out through ``simplyp_calibrate_host``.  Returns (stats [M][V][10], diag [M][S][4])."""
     lib = require_device()
     forcing = _c64(forcing)
     member_params = _c64(member_params)
@@ -196,8 +207,8 @@ def calibrate_host(forcing, member_params, sc_params, parent_offsets, parent_ids
     V = obs.shape[0]
     po, pid = _topology_arrays(parent_offsets, parent_ids)
     dims = make_dims(M, S, D, Msc, V, int(po[-1]))
-    stats = np.empty((M, V, pk.NSTAT), dtype=np.float64)
-    diag = np.zeros((M, S, pk.NDIAG), dtype=np.int64)
+    stats = _result_buffer(stats, (M, V, pk.NSTAT), np.float64)
+    diag = _result_buffer(diag, (M, S, pk.NDIAG), np.int64)
     rc = lib.simplyp_calibrate_host(device, C.byref(dims), C.byref(opt), _dptr(forcing), _dptr(member_params),
                                     _dptr(sc_params), _iptr(po), _iptr(pid), _dptr(obs), _iptr(obs_desc),
                                     _dptr(stats), diag.ctypes.data_as(C.POINTER(C.c_int64)) if want_diag else None)

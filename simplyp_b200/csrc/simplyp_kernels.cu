@@ -163,6 +163,12 @@ __device__ __forceinline__ void tma_load_tile(ForcingRing* ring, int slot, const
 }
 
 // ------------------------------------------------------------------------------------------ IO policies
+// ROUTED = the network build of the kernel (reach routing: progress flags, parents' fluxes).  It is a compile-time
+// property on purpose: an ensemble of one sub-catchment must not even contain the routing loops — besides their cost,
+// control flow whose convergence ptxas cannot prove (loops over a thread's own parent list that are left from the
+// middle, the per-thread level search) made it guard EVERY quad shuffle of the step loop with a divergence check and
+// copy each shuffled register pair (673 instead of ~600 instructions per step attempt, profiles/r02_step_loop.sass).
+template <bool ROUTED>
 struct IOBase {
   const KArgs& a;
   int m, s;
@@ -174,12 +180,16 @@ struct IOBase {
       : a(a_), m(m_), s(s_), scp_member(a_.sc_params + (size_t)(a_.Msc > 1 ? m_ : 0) * a_.S * SIMPLYP_NP_SC),
         ring(ring_), my_tile(-1), wait_status(0) {}
 
-  // forcing tile of `day` resident?  Warp-granular: all lanes call it with the same `day`; the ring's consumers are
-  // the warps of the block and lane 0 does the bookkeeping (on a tile change the warp first leaves its old tile, once).
-  __device__ __forceinline__ bool forcing_ready_warp(int day) {
+  // The warp enters the forcing tile of `day` (all lanes call it with the same `day`; the ring's consumers are the
+  // warps of the block and lane 0 does the bookkeeping): on a tile change it first leaves its old tile — the last
+  // warp out re-arms the slot and starts the copy of tile k+FORC_SLOTS into it — and then waits for the new tile's
+  // mbarrier.  Every branch and loop condition here is a warp vote, i.e. provably warp-uniform: with thread-varying
+  // conditions around the lane-0 region ptxas could not prove the warp converged afterwards and guarded every
+  // shuffle of the step loop with a divergence check plus register copies (+12 % instructions per step attempt).
+  __device__ __forceinline__ bool enter_tile(int day, long long t0, long long limit) {
     const int q = day / FORC_TILE;
-    if (q != my_tile) {
-      if (my_tile >= 0 && my_tile == q - 1) {
+    if (__any_sync(0xffffffffu, q != my_tile)) {
+      if (__any_sync(0xffffffffu, my_tile >= 0 && my_tile == q - 1)) {
         __syncwarp();                                         // every lane is done reading the old tile
         if ((threadIdx.x & 31) == 0) {
           const int slot = (my_tile - ring->first_tile) % FORC_SLOTS;
@@ -190,25 +200,33 @@ struct IOBase {
             if (next * FORC_TILE < ring->end_day) tma_load_tile(ring, slot, a.forcing, next, a.D);
           }
         }
-        my_tile = -2 - q;
+        __syncwarp();
       }
       const int rel = q - ring->first_tile;
-      if (!mbar_test_parity(&ring->full[rel % FORC_SLOTS], (unsigned)(rel / FORC_SLOTS) & 1u)) return false;
+      bool ok = true;
+      while (ok && !__all_sync(0xffffffffu, mbar_test_parity(&ring->full[rel % FORC_SLOTS], (unsigned)(rel / FORC_SLOTS) & 1u)))
+        ok = __all_sync(0xffffffffu, (clock64() - t0) < limit);
       my_tile = q;
+      return ok;
     }
     return true;
   }
-  // upstream reaches of this item have published `day`?
+  // upstream reaches of this item have published `day`?  The loop over the item's own parent list runs a
+  // WARP-UNIFORM number of times (the longest list in the warp, lanes past their own list idle): a loop whose trip
+  // count varies between the lanes is another shape that costs ptxas its convergence proof (see IOBase).
   __device__ __forceinline__ bool upstream_ready(int day) const {
-    if (a.progress == nullptr) return true;
-    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
-    for (int e = e0; e < e1; ++e) {
-      const int* flag = a.progress + (size_t)m * a.S + a.parent_ids[e];
-      int done;
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(flag) : "memory");
-      if (done <= day) return false;
+    const int e0 = a.parent_offsets[s], n = a.parent_offsets[s + 1] - e0;
+    const int n_max = __reduce_max_sync(0xffffffffu, n);
+    int oldest = 0x7fffffff;
+    for (int k = 0; k < n_max; ++k) {
+      if (k < n) {
+        const int* flag = a.progress + (size_t)m * a.S + a.parent_ids[e0 + k];
+        int done;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(flag) : "memory");
+        oldest = done < oldest ? done : oldest;
+      }
     }
-    return true;
+    return oldest > day;
   }
   // quad program: block (the whole warp) until forcing and upstream inputs of `day` exist
   // A watchdog (2^37 cycles, about 70 s of SM clock) turns a wait that can never end (a bug, or a launch that
@@ -218,9 +236,8 @@ struct IOBase {
   __device__ __forceinline__ void wait(int day) {
     const long long limit = 1ll << 37;
     const long long t0 = clock64();
-    bool ok = true;
-    while (ok && !forcing_ready_warp(day)) ok = (clock64() - t0) < limit;
-    if (a.progress != nullptr) {
+    bool ok = enter_tile(day, t0, limit);
+    if (ROUTED && a.progress != nullptr) {
       unsigned ns = 32;
       while (ok && !__all_sync(0xffffffffu, upstream_ready(day))) {
         __nanosleep(ns);
@@ -233,7 +250,7 @@ struct IOBase {
 
   // release store that pairs with the acquire load in upstream_ready()
   __device__ __forceinline__ void publish(int day) const {
-    if (a.progress == nullptr) return;
+    if (!ROUTED || a.progress == nullptr) return;
     int* flag = a.progress + (size_t)m * a.S + s;
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(day + 1) : "memory");
   }
@@ -249,21 +266,27 @@ struct IOBase {
 
 // Full-output mode: parents' fluxes are read back from their output rows (columns Qr, Msus_kg/day,
 // TDP_kg/day, PP_kg/day — exactly what the reference reads from df_R_dict, model.py:524-528).
-struct RunIO : IOBase {
-  using IOBase::IOBase;
+template <bool ROUTED>
+struct RunIO : IOBase<ROUTED> {
+  using B = IOBase<ROUTED>;
+  using B::a; using B::m; using B::s; using B::scp_member;
+  __device__ RunIO(const KArgs& a_, int m_, int s_, ForcingRing* ring_) : B(a_, m_, s_, ring_) {}
   __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
     us[0] = us[1] = us[2] = us[3] = 0.0;
-    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
-    if (e0 == e1) return;
+    if (!ROUTED) return;
+    const int e0 = a.parent_offsets[s], n = a.parent_offsets[s + 1] - e0;
+    const int n_max = __reduce_max_sync(0xffffffffu, n);       // warp-uniform trip count, see upstream_ready()
     const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-    for (int e = e0; e < e1; ++e) {
-      const int p = a.parent_ids[e];
-      const double* row = a.out + (((size_t)m * a.S + p) * a.D + day) * SIMPLYP_NOUT;
-      const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-      us[0] += __ldcg(row + SIMPLYP_O_QR) * (A_up / A_this);   // :525
-      us[1] += __ldcg(row + SIMPLYP_O_MSUS_FLUX);
-      us[2] += __ldcg(row + SIMPLYP_O_TDP_FLUX);
-      us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
+    for (int k = 0; k < n_max; ++k) {
+      if (k < n) {
+        const int p = a.parent_ids[e0 + k];
+        const double* row = a.out + (((size_t)m * a.S + p) * a.D + day) * SIMPLYP_NOUT;
+        const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+        us[0] += __ldcg(row + SIMPLYP_O_QR) * (A_up / A_this);   // :525
+        us[1] += __ldcg(row + SIMPLYP_O_MSUS_FLUX);
+        us[2] += __ldcg(row + SIMPLYP_O_TDP_FLUX);
+        us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
+      }
     }
   }
   __device__ __forceinline__ void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
@@ -295,25 +318,31 @@ struct RunIO : IOBase {
 constexpr int STAT_SLOTS = 6;
 constexpr int STAT_STRIDE = STAT_SLOTS * 8 + 1;      // doubles per item; odd: the 8 quad leaders of a warp hit distinct banks
 
-struct CalIO : IOBase {
+template <bool ROUTED>
+struct CalIO : IOBase<ROUTED> {
+  using B = IOBase<ROUTED>;
+  using B::a; using B::m; using B::s; using B::scp_member;
   double f_TDP;
   double* sacc;     // shared-memory accumulators of this item [STAT_SLOTS][8], or null
   __device__ CalIO(const KArgs& a_, int m_, int s_, ForcingRing* ring_, double f_TDP_, double* sacc_ = nullptr)
-      : IOBase(a_, m_, s_, ring_), f_TDP(f_TDP_), sacc(sacc_) {}
+      : B(a_, m_, s_, ring_), f_TDP(f_TDP_), sacc(sacc_) {}
 
   __device__ __forceinline__ void upstream(int day, double (&us)[4]) const {
     us[0] = us[1] = us[2] = us[3] = 0.0;
-    const int e0 = a.parent_offsets[s], e1 = a.parent_offsets[s + 1];
-    if (e0 == e1) return;
+    if (!ROUTED) return;
+    const int e0 = a.parent_offsets[s], n = a.parent_offsets[s + 1] - e0;
+    const int n_max = __reduce_max_sync(0xffffffffu, n);       // warp-uniform trip count, see upstream_ready()
     const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-    for (int e = e0; e < e1; ++e) {
-      const int p = a.parent_ids[e];
-      const double* row = a.flux + (((size_t)m * a.S + p) * a.D + day) * 4;
-      const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-      us[0] += __ldcg(row + 0) * (A_up / A_this);
-      us[1] += __ldcg(row + 1);
-      us[2] += __ldcg(row + 2);
-      us[3] += __ldcg(row + 3);
+    for (int k = 0; k < n_max; ++k) {
+      if (k < n) {
+        const int p = a.parent_ids[e0 + k];
+        const double* row = a.flux + (((size_t)m * a.S + p) * a.D + day) * 4;
+        const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+        us[0] += __ldcg(row + 0) * (A_up / A_this);
+        us[1] += __ldcg(row + 1);
+        us[2] += __ldcg(row + 2);
+        us[3] += __ldcg(row + 3);
+      }
     }
   }
   __device__ __forceinline__ void emit(int day, const double (&)[NL], double, const double (&acc)[NA],
@@ -448,7 +477,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     __syncthreads();
     vblock = s_vblock;
     if (vblock < 0) return;
-  } else if (a.ticket != nullptr) {
+  } else if (STIFF && a.ticket != nullptr) {
     if (threadIdx.x == 0) s_vblock = (int)atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
     __syncthreads();
     vblock = s_vblock;
@@ -461,7 +490,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     // grid is sized from a host-side upper bound, so trailing warps — and whole blocks — may have nothing to do.
     // They leave before the forcing ring counts them as consumers (a warp is either all in range or all out of it).
     int n_warps = blockDim.x >> 5;
-    if (a.level_item_off != nullptr) {
+    if (STIFF && a.level_item_off != nullptr) {
       const long long rest = a.level_item_off[a.n_levels] - (long long)vblock * quads_per_block;
       if (rest <= 0) return;
       if (rest < (long long)quads_per_block) n_warps = (int)((rest + 7) >> 3);
@@ -481,25 +510,35 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     long long idx = (long long)vblock * quads_per_block + (threadIdx.x >> 2);
     bool valid;
     int w, m;
-    if (a.level_item_off == nullptr) {               // one sub-catchment: items are the members
+    if (!STIFF || a.level_item_off == nullptr) {     // one sub-catchment: items are the members
       valid = idx < a.M;
       if (!valid) idx = a.M - 1;                     // padding quads shadow the last item and write nothing
       w = 0;
       m = a.perm ? a.perm[idx] : (int)idx;
     } else {
-      int lo = 0, hi = a.n_levels;                   // level with level_item_off[lo] <= idx < level_item_off[lo+1]
-      while (hi - lo > 1) {
+      // group with level_item_off[lo] <= idx < level_item_off[lo+1]: bisection with a warp-uniform trip count and
+      // selects instead of branches (once lo + 1 == hi the midpoint is lo itself and nothing moves any more)
+      int lo = 0, hi = a.n_levels;
+      for (int span = a.n_levels; span > 1; span = (span + 1) >> 1) {
         const int mid = (lo + hi) >> 1;
-        if (a.level_item_off[mid] <= idx) lo = mid; else hi = mid;
+        const bool right = a.level_item_off[mid] <= idx;
+        lo = right ? mid : lo;
+        hi = right ? hi : mid;
       }
       long long local = idx - a.level_item_off[lo];
       const int o0 = a.level_order_off[lo];
       const long long n_real = (long long)(a.level_order_off[lo + 1] - o0) * a.M;
       valid = local < n_real;
-      if (!valid) local = n_real - 1;
-      const int wl = (int)(local / a.M);
+      local = valid ? local : n_real - 1;
+      // local = wl * M + m without a 64-bit integer division (a subroutine call with a divergent slow path: the other
+      // construct that cost the step loop its convergence proof): the quotient from a double product — exact to
+      // within one, local < 2^53 — then one correction step with selects
+      int wl = (int)(((double)local + 0.5) * sp_rcp((double)a.M));
+      long long rem = local - (long long)wl * a.M;
+      wl += (rem >= a.M) ? 1 : ((rem < 0) ? -1 : 0);
+      rem = local - (long long)wl * a.M;
       w = o0 + wl;
-      m = (int)(local - (long long)wl * a.M);
+      m = (int)rem;
     }
     const int s = a.work_sc ? a.work_sc[w] : w;
 
@@ -530,7 +569,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     QuadMem& qm = qmem[threadIdx.x >> 2];
     ThreadCounters cnt;
     if (MODE == MODE_CAL) {
-      CalIO io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
+      CalIO<STIFF> io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
       run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
       if (valid && q.ql == 0) {
         if (a.pilot_pass) {
@@ -542,7 +581,7 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
       }
       cnt.status |= io.wait_status;
     } else {
-      RunIO io(a, m, s, ring);
+      RunIO<STIFF> io(a, m, s, ring);
       run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
       cnt.status |= io.wait_status;
     }
@@ -807,7 +846,10 @@ __global__ void thornthwaite_kernel(int D, int NM, const double* t_air, int t_st
   }
   __syncthreads();
   for (int m = threadIdx.x; m < NM; m += blockDim.x) {
-    const int y = m / 12, mon = m % 12, leap = year_is_leap[y] != 0;
+    // bit 0: the year is a leap year (days of February); bit 1: the year takes the leap-year daylight table — the
+    // reference keeps that table for every year AFTER its first leap year too (inputs.py:269-273 overwrites the
+    // variable the non-leap branch reads), so the host sets bit 1 accordingly under strict quirks
+    const int y = m / 12, mon = m % 12, leap = year_is_leap[y] & 1, dl = (year_is_leap[y] >> 1) & 1;
     double heat = 0.0;
     for (int k = 0; k < 12; ++k) {
       const double x = s_tmean[12 * y + k] / 5.0;
@@ -816,7 +858,7 @@ __global__ void thornthwaite_kernel(int D, int NM, const double* t_air, int t_st
     const double a = (6.75e-07 * pow(heat, 3.0)) - (7.71e-05 * pow(heat, 2.0)) + (1.792e-02 * heat) + 0.49239;
     const double N = mdays[mon] + ((leap && mon == 1) ? 1 : 0);
     const double ta = s_tmean[m];
-    s_pet[m] = (1.6 * (s_dlh[leap][mon] / 12.0) * (N / 30.0) * pow(10.0 * ta / heat, a) * 10.0) / N;
+    s_pet[m] = (1.6 * (s_dlh[dl][mon] / 12.0) * (N / 30.0) * pow(10.0 * ta / heat, a) * 10.0) / N;
   }
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += blockDim.x) {

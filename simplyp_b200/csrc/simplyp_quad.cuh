@@ -120,9 +120,13 @@ struct QuadDev {
   __device__ __forceinline__ T splat(double x) const { return x; }
   __device__ __forceinline__ T bcast(T x, int src) const {
     // the two halves are shuffled as ints: __shfl_sync(double) makes ptxas swap the register pair afterwards
+#ifdef SP_BCAST_DOUBLE
+    return __shfl_sync(0xffffffffu, x, src, 4);
+#else
     const int lo = __shfl_sync(0xffffffffu, __double2loint(x), src, 4);
     const int hi = __shfl_sync(0xffffffffu, __double2hiint(x), src, 4);
     return __hiloint2double(hi, lo);
+#endif
   }
   __device__ __forceinline__ T sum(T x) const {
     x += __shfl_xor_sync(0xffffffffu, x, 1);
@@ -144,7 +148,11 @@ struct QuadCoef {
   T eY, eU;                    // own exponential: exp(eY*yA + eU*u)
   T p1, p0, g0, g1;            // own gate: w = p1*yA + p0 ; G = g0 + f(w)*w*g1   (f = smoothstep on [0,1])
   T a0, aE, aSA, aSS, aG, aR;  // slot A: L = a0 + aE*e + aSA*QsA + aSS*QsS + aG*Qg + aR*Qr ; dA = L*(m0 + mA/Vr)
+  T aRE;                       //   aE (lanes 0-2) and aR (lane 3) in one coefficient of the own exponential: lane 3's
+                               //   own exponential IS Qr, and its aE is zero like the other lanes' aR
   T m0, mA;                    //   lanes 0-2: (1, 0) ; lane 3: (0, 1/(1-b_Q))  -> du/dt = net/((1-b_Q) Vr)
+  T rvOff;                     //   added to slot B before the reciprocal: 0 on lane 3 (1/Vr), 1 elsewhere (the other
+                               //   lanes' mA is zero; the offset only keeps their unused reciprocal finite)
   T b0, bK, bSA, bSS, bG;      // slot B: dB = b0 + bK*Qr^k + bSA*QsA + bSS*QsS + bG*Qg - yB*Qr/Vr
 };                             //   lane 3 (yB = Vr): yB*Qr/Vr = Qr, so its b-coefficients spell net + Qr (:127,131)
 
@@ -167,8 +175,9 @@ SP_HD void quad_static_coef(const Q& q, const Hot& h, QuadCoef<Q>& c) {
   c.aR = q.pick(0.0, 0.0, 0.0, -1.0);
   c.m0 = q.pick(1.0, 1.0, 1.0, 0.0);
   c.mA = q.pick(0.0, 0.0, 0.0, 1.0 / (1.0 - h.bQ));
+  c.rvOff = q.pick(1.0, 1.0, 1.0, 0.0);
   c.bG = q.pick(0.0, h.tG, 0.0, 1.0);                            // :163 ; lane 3: +Qg
-  c.a0 = c.aE = c.b0 = c.bK = c.bSA = c.bSS = q.splat(0.0);
+  c.a0 = c.aE = c.aRE = c.b0 = c.bK = c.bSA = c.bSS = q.splat(0.0);
 }
 
 // Coefficients that follow the day's forcing, upstream inputs and soil-P carry (filled by begin_day in h).
@@ -176,6 +185,7 @@ template <class Q>
 SP_HD void quad_daily_coef(const Q& q, const Hot& h, QuadCoef<Q>& c) {
   c.a0 = q.pick(h.Pin - h.aE, h.Pin - h.aE, 0.0, h.qin0);        // :106,110 ; :127
   c.aE = q.pick(h.aE, h.aE, 0.0, 0.0);
+  c.aRE = q.pick(h.aE, h.aE, 0.0, -1.0);
   const double omb = 1.0 - h.beta;
   c.b0 = q.pick(h.MsusUS, h.t0, h.PPUS, h.qin0);                 // :144, :165-166, :177 ; lane 3: :127
   c.bK = q.pick(h.cM, 0.0, h.cP, 0.0);                           // :138-143, :171-176
@@ -191,19 +201,20 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   // Source order = intended issue order (ptxas keeps independent chains roughly where they are written): the gated
   // flows depend on the lane's own state only, so they are computed and broadcast FIRST; the exponential, which
   // waits for the broadcast of u, then has only its own two broadcasts behind it.
+  // Six quad broadcasts: u, the three gated flows, Qr^k_M and the outflow rate Qr/Vr.  Lane 3 owns both Qr (its
+  // exponential) and Vr (its slot B), so it forms Qr/Vr itself and nobody else needs Vr or Qr.
   const T w = qfma(c.p1, yA, c.p0);
   const T G = qfma(qgate(w) * w, c.g1, c.g0);
   const T u = q.bcast(yA, 3);
-  const T Vr = q.bcast(yB, 3);
-  const T rV = qrcp40(Vr);                  // 40 bits: the integration tolerance is 1e-7
+  const T rV = qrcp40(yB + c.rvOff);        // lane 3: 1/Vr to 40 bits (the integration tolerance is 1e-7)
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
   e = q.exp(qfma(c.eY, yA, c.eU * u));
   const T gsum = qfma(c.aG, Qg, qfma(c.aSA, QsA, qfma(c.aSS, QsS, c.a0)));   // ready before the exponential
   const T src0 = qfma(c.bSA, QsA, qfma(c.bSS, QsS, qfma(c.bG, Qg, c.b0)));
   const T mult = qfma(rV, c.mA, c.m0);
-  const T qk = q.bcast(e, 2), Qr = q.bcast(e, 3);
-  const T L = qfma(c.aR, Qr, qfma(c.aE, e, gsum));
-  const T r = Qr * rV;                       // Qr/Vr
+  const T qk = q.bcast(e, 2);
+  const T r = q.bcast(e * rV, 3);           // Qr/Vr
+  const T L = qfma(c.aRE, e, gsum);
   const T out = yB * r;                      // outflow of the lane's in-stream mass (:145,147,166,168,178,180)
   dA = L * mult;                             // lane 3: du/dt = net/((1-b_Q) Vr)
   dB = qfma(c.bK, qk, src0) - out;           // lane 3: out = Vr*Qr/Vr = Qr, src = net + Qr -> dVr/dt = net (:131)
@@ -511,6 +522,9 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
 
     // ---- step loop: lock-step over the quads of a warp ------------------------------------------
     while (q.any(active)) {
+#ifdef SP_LOOP_SYNCWARP
+      q.sync();
+#endif
 #ifdef SP_TIMELINE
       ++sp_lockstep_iters;                        // analysis builds: attempts the WARP executed (lock-step)
 #endif

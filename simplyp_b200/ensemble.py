@@ -91,27 +91,68 @@ def shard_bounds(n_members, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+class GatherBuffers:
+    """Pre-allocated buffers of the one collective of the path: the all-gather of the per-member fit statistics.
+
+    ``local`` is this rank's slot INSIDE the gather buffer — hand it to ``Engine.calibrate(stats=...)`` and the kernel
+    writes its statistics where the collective reads them; ``gather()`` is then one ``all_gather_into_tensor`` with no
+    allocation, no padding copy and (when the shards are equal) no concatenation: the returned tensor is the buffer.
+    NCCL gathers in place (send buffer = own slot of the receive buffer); gloo (CPU tests) gets a copy of the slot.
+    """
+
+    def __init__(self, n_members, tail_shape, device, dtype=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.n_members = int(n_members)
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.sizes = [shard_bounds(self.n_members, self.world, r) for r in range(self.world)]
+        self.mmax = max(hi - lo for lo, hi in self.sizes)
+        self.equal = all(hi - lo == self.mmax for lo, hi in self.sizes)
+        dtype = torch.float64 if dtype is None else dtype
+        self.buffer = torch.zeros((self.world * self.mmax,) + tuple(tail_shape), dtype=dtype, device=device)
+        lo, hi = self.sizes[self.rank]
+        self.slot = self.buffer[self.rank * self.mmax:(self.rank + 1) * self.mmax]
+        self.local = self.slot[:hi - lo]
+        self.compact = None if self.equal else torch.empty((self.n_members,) + tuple(tail_shape), dtype=dtype, device=device)
+
+    def gather(self):
+        """All ranks' statistics, [M][...] in member order (a view of the buffer when the shards are equal)."""
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            src = self.slot if self.buffer.is_cuda else self.slot.clone()
+            dist.all_gather_into_tensor(self.buffer, src, group=self.group)
+        if self.equal:
+            return self.buffer
+        torch.cat([self.buffer[r * self.mmax: r * self.mmax + (hi - lo)] for r, (lo, hi) in enumerate(self.sizes)],
+                  dim=0, out=self.compact)
+        return self.compact
+
+
+_gather_cache = {}
+
+
 def all_gather_stats(local_stats, n_members, group=None):
     """All-gather the per-member statistics [M_local][V][10] of every rank into [M][V][10] (rank order).
 
-    Uses ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).  Blocks are padded to the largest
-    shard so one ``all_gather_into_tensor`` suffices.
+    Uses ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) through a cached :class:`GatherBuffers`; callers
+    that run many passes should hold a ``GatherBuffers`` themselves and let the kernel write into ``.local``.
     """
-    import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
         return local_stats
-    world = dist.get_world_size(group)
-    sizes = [shard_bounds(n_members, world, r) for r in range(world)]
-    mmax = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((mmax,) + tuple(local_stats.shape[1:]), dtype=local_stats.dtype, device=local_stats.device)
-    pad[: local_stats.shape[0]] = local_stats
-    gathered = torch.empty((world * mmax,) + tuple(local_stats.shape[1:]), dtype=local_stats.dtype,
-                           device=local_stats.device)
-    dist.all_gather_into_tensor(gathered, pad, group=group)
-    parts = [gathered[r * mmax: r * mmax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
-    return torch.cat(parts, dim=0)
+    key = (int(n_members), tuple(local_stats.shape[1:]), str(local_stats.device), local_stats.dtype, id(group))
+    gb = _gather_cache.get(key)
+    if gb is None:
+        gb = _gather_cache[key] = GatherBuffers(n_members, local_stats.shape[1:], local_stats.device, local_stats.dtype, group)
+    gb.local.copy_(local_stats)
+    return gb.gather()
 
 
 def calibrate_ensemble(met_df, p_struc, p_SU, p_LU, p_SC, p, dynamic_options, obs_dict, samples,

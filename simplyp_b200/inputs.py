@@ -290,9 +290,24 @@ def annual_thornthwaite(monthly_t, monthly_mean_dlh, year=None):
             for ta, L, N in zip(adj, monthly_mean_dlh, month_days)]
 
 
-def daily_PET(latitude, met_df):
+def _daylight_table_is_leap(years, strict_reference_quirks):
+    """Per year: does Thornthwaite's day-length factor use the leap-year table?  The reference picks the table with
+    ``monthly_mean_dlh = monthly_mean_dlh_leap`` in the leap branch and ``monthly_mean_dlh = monthly_mean_dlh`` in the
+    other (``inputs.py:269-273``): the first leap year overwrites the variable the non-leap branch keeps, so every
+    later year uses the leap-year table too (up to 0.5 % in March-December).  Reproduced under strict quirks."""
+    out, seen = [], False
+    for y in years:
+        leap = calendar.isleap(int(y))
+        seen = seen or leap
+        out.append(seen if strict_reference_quirks else leap)
+    return out
+
+
+def daily_PET(latitude, met_df, strict_reference_quirks=True):
     """Daily PET [mm/day] from ``T_air`` by Thornthwaite, monthly values placed on the 16th of
-    each month and linearly interpolated to days (reference ``inputs.py:232-312``).
+    each month and linearly interpolated to days (reference ``inputs.py:232-312``; pinned to the unmodified
+    reference wrapper by ``tests/golden/ref_pet_daily.npz``).  ``strict_reference_quirks=False`` picks the
+    daylight-hours table by the calendar instead of the reference's sticky choice.
     """
     latitude = deg2rad(latitude)
     dlh_normal = monthly_mean_daylight_hours(latitude, year=1983)
@@ -300,13 +315,14 @@ def daily_PET(latitude, met_df):
 
     t_month = met_df["T_air"].groupby([met_df.index.year, met_df.index.month]).mean()
     pet_m = []
-    for year in sorted(set(met_df.index.year)):
+    years = sorted(set(met_df.index.year))
+    for year, use_leap in zip(years, _daylight_table_is_leap(years, strict_reference_quirks)):
         vals = t_month.loc[year].to_numpy()
         if len(vals) < 12:
             raise ValueError("PET calc requires input met data for whole calendar years."
                              "Year {0!r} does not contain 12 months. Check input met data,"
                              "or change the start/end dates in the parameter file".format(year))
-        dlh = dlh_leap if calendar.isleap(year) else dlh_normal
+        dlh = dlh_leap if use_leap else dlh_normal
         pet_m.extend(annual_thornthwaite(vals, dlh, year=year))
 
     start = met_df.index[0].date()
@@ -322,7 +338,7 @@ def daily_PET(latitude, met_df):
     return met_df
 
 
-def daily_PET_device(latitude, met_df, engine=None):
+def daily_PET_device(latitude, met_df, engine=None, strict_reference_quirks=True):
     """:func:`daily_PET` with the arithmetic on the GPU (``thornthwaite_kernel`` behind the C-ABI entry point
     ``simplyp_thornthwaite_pet_device``): same arguments, same returned frame, same ``ValueError`` for a record
     that is not made of whole calendar years (reference ``inputs.py:232-312``).  No CPU fallback."""
@@ -339,7 +355,8 @@ def daily_PET_device(latitude, met_df, engine=None):
                              "Year {0!r} does not contain 12 months. Check input met data,"
                              "or change the start/end dates in the parameter file".format(year))
     month_start = np.concatenate([[0], np.cumsum(counts.to_numpy())]).astype(np.int32)
-    leap = np.array([1 if calendar.isleap(y) else 0 for y in years], dtype=np.int32)
+    leap = np.array([(1 if calendar.isleap(y) else 0) | (2 if t else 0)
+                     for y, t in zip(years, _daylight_table_is_leap(years, strict_reference_quirks))], dtype=np.int32)
     eng = engine or Engine()
     pet = eng.thornthwaite_pet(met_df["T_air"].to_numpy(dtype=np.float64, copy=True), month_start, leap, float(latitude))
     out = met_df.drop(columns=["PET"]) if "PET" in met_df.columns else met_df.copy()

@@ -78,3 +78,36 @@ def synthetic_met(n_days, start="1981-01-01", seed=11, p_wet=0.55):
     pet = np.clip(1.5 + 1.4 * np.sin(2 * np.pi * (doy - 105) / 365.25), 0.1, None)
     return pd.DataFrame({"T_air": np.round(t_air, 2), "PET": np.round(pet, 2), "Precipitation": np.round(rain, 2)},
                         index=idx)
+
+
+def scale_config(cfg, members=1, n_days=None):
+    """BASELINE.json configs 3 and 5 as the reference's pandas objects plus the packed arrays.
+
+    config 3: 256-sub-catchment branching network (seed 3), 30 years (10,958 days) of seeded synthetic forcing, both
+    dynamic options on; config 5: 4096 sub-catchments with all three land-use classes present, 50 years (18,262
+    days).  Parameters are Tarland's; with ``members`` > 1 the members differ in ``a_Q`` (0.8x .. 1.2x).  ``n_days``
+    truncates the record (parity windows).  Returns a dict: p_SU, dyn, p, p_LU, p_SC, p_struc, met (pandas), topo,
+    opt, member [M][40], sc [1][S][16], forcing [D][4].
+    """
+    from . import inputs as spi, model as spm, packing as pk, tarland
+    p_SU, dyn, p, p_LU, p_SC0, _p_struc0, _met, _obs = tarland.load(dynamic="y")
+    if cfg == 3:
+        n_sc, days, all_lu = 256, 10958, False
+    elif cfg == 5:
+        n_sc, days, all_lu = 4096, 18262, True
+    else:
+        raise ValueError("scale_config: cfg must be 3 or 5")
+    p, p_SC, p_struc = random_network(p, p_SC0[1], n_sc=n_sc, seed=3, all_land_uses=all_lu)
+    met = synthetic_met(days, seed=11)
+    met = spi.snow_hydrol_inputs(p["D_snow_0"], p["f_DDSM"], met)
+    if n_days is not None:
+        met = met.iloc[:int(n_days)]
+    pk.validate_land_use(p_SC, p["SC_list"])
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    member = np.repeat(pk.member_vector(p, p_LU)[None], members, axis=0)
+    if members > 1:
+        member[:, pk.MEMBER_INDEX["a_Q"]] *= np.linspace(0.8, 1.2, members)
+    sc = pk.sc_matrix(p_SC, topo.sc_ids)[None]
+    return dict(p_SU=p_SU, dyn=dyn, p=p, p_LU=p_LU, p_SC=p_SC, p_struc=p_struc, met=met, topo=topo, opt=opt,
+                member=member, sc=sc, forcing=pk.forcing_matrix(met))

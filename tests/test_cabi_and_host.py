@@ -330,6 +330,18 @@ full = torch.arange(M * V * 10, dtype=torch.float64).reshape(M, V, 10)
 lo, hi = ens.shard_bounds(M, 2, dist.get_rank())
 got = ens.all_gather_stats(full[lo:hi].clone(), M)
 assert got.shape == full.shape and torch.equal(got, full), (got.shape, lo, hi)
+# pre-allocated buffers (what bench.py holds): the producer writes into .local, gather() allocates nothing;
+# ragged shards (11 = 6 + 5) are compacted, equal ones (12 = 6 + 6) come back as the buffer itself
+for M2 in (11, 12):
+    full2 = torch.arange(M2 * V * 10, dtype=torch.float64).reshape(M2, V, 10) + 0.5
+    gb = ens.GatherBuffers(M2, (V, 10), "cpu")
+    lo, hi = ens.shard_bounds(M2, 2, dist.get_rank())
+    assert gb.local.shape[0] == hi - lo
+    for rep in range(2):
+        gb.local.copy_(full2[lo:hi] + rep)
+        out = gb.gather()
+        assert torch.equal(out, full2 + rep), (M2, rep)
+    assert (out.data_ptr() == gb.buffer.data_ptr()) == (M2 == 12)
 dist.destroy_process_group()
 print("ok", dist.get_rank() if dist.is_initialized() else "")
 ''' % ROOT
