@@ -289,23 +289,22 @@ struct RunIO : IOBase<ROUTED> {
       }
     }
   }
-  __device__ __forceinline__ void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
+  // K2: the 200-byte output row out[m][s][day][0:25] (the reference's 12 + 13 raw columns, model.py:737-745).  Every
+  // lane of the quad holds the whole row (the day-boundary algebra is redundant across the quad), so the four lanes
+  // store it together: lane l writes columns l, l+4, l+8, ... — each store instruction of the warp moves eight
+  // contiguous 32-byte pieces (one per quad) instead of eight single doubles, 7 store instructions per day instead
+  // of 25 by the leader alone.  The column a lane stores is chosen with selects, not by indexing a register array.
+  template <class Q>
+  __device__ __forceinline__ void emit(const Q& q, int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
                                        const double (&non)[13], const Cold&) const {
-    double* row = a.out + (((size_t)m * a.S + s) * a.D + day) * SIMPLYP_NOUT;
-    row[SIMPLYP_O_VSA] = y[iVsA];
-    row[SIMPLYP_O_VSS] = y[iVsS];
-    row[SIMPLYP_O_VG] = y[iVg];
-    row[SIMPLYP_O_VR] = Vr;
-    row[SIMPLYP_O_QR_END] = y[iQr];
-    row[SIMPLYP_O_QR] = acc[0];
-    row[SIMPLYP_O_MSUS_END] = y[iMsus];
-    row[SIMPLYP_O_MSUS_FLUX] = acc[1];
-    row[SIMPLYP_O_TDPR_END] = y[iTDPr];
-    row[SIMPLYP_O_TDP_FLUX] = acc[2];
-    row[SIMPLYP_O_PPR_END] = y[iPPr];
-    row[SIMPLYP_O_PP_FLUX] = acc[3];
+    double* row = a.out + (((size_t)m * a.S + s) * a.D + day) * SIMPLYP_NOUT + q.ql;
+    const double r[28] = {y[iVsA], y[iVsS], y[iVg], Vr, y[iQr], acc[0], y[iMsus], acc[1], y[iTDPr], acc[2], y[iPPr], acc[3],
+                          non[0], non[1], non[2], non[3], non[4], non[5], non[6], non[7], non[8], non[9], non[10], non[11],
+                          non[12], 0.0, 0.0, 0.0};
+    static_assert(SIMPLYP_O_QQ == 12 && SIMPLYP_NOUT == 25 && SIMPLYP_O_VR == 3 && SIMPLYP_O_PP_FLUX == 11, "row layout");
 #pragma unroll
-    for (int i = 0; i < 13; ++i) row[SIMPLYP_O_QQ + i] = non[i];
+    for (int i = 0; i < 6; ++i) row[4 * i] = q.pick(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    if (q.ql == 0) row[24] = r[24];
   }
 };
 
@@ -345,16 +344,22 @@ struct CalIO : IOBase<ROUTED> {
       }
     }
   }
-  __device__ __forceinline__ void emit(int day, const double (&)[NL], double, const double (&acc)[NA],
+  template <class Q>
+  __device__ __forceinline__ void emit(const Q& q, int day, const double (&)[NL], double, const double (&acc)[NA],
                                        const double (&)[13], const Cold& c) const {
+    if (!q.leader()) return;
     if (a.flux != nullptr) {
       double* row = a.flux + (((size_t)m * a.S + s) * a.D + day) * 4;
       row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = acc[3];
     }
-    // simulated concentrations (model.py:784-793, :840-845): (flux/Qr)/A_catch
+    // simulated counterparts of the observed series (model.py:784-793, :840-845): Q_cumecs = Qr*A*1000/86400,
+    // concentrations (flux/Qr)/A_catch.  With rank statistics they are formed in the reference's own order of
+    // operations with IEEE divisions: Spearman's r is sensitive to the last bit wherever simulated values tie
+    // (recession days at the groundwater floor; measured 2e-6 on 13,700 pairs).  Without them two reciprocals serve all
+    // series (last-bit differences mean 1e-16 in NSE and the likelihood; the divisions cost 2 % of the run time).
     const double A = c.A_catch;
-    const double iq = sp_rcp(acc[0]) * sp_rcp(A);
-    const double tdp = acc[2] * iq, pp = acc[3] * iq;
+    const bool exact = a.sim_obs != nullptr;
+    const double iq = exact ? 0.0 : sp_rcp(acc[0]) * sp_rcp(A);
     int slot = 0;
     for (int v = 0; v < a.V; ++v) {
       if (__ldg(a.obs_desc + 2 * v) != s) continue;
@@ -363,13 +368,24 @@ struct CalIO : IOBase<ROUTED> {
       if (o != o) continue;  // no observation that day
       const int kind = __ldg(a.obs_desc + 2 * v + 1);
       double sim;
-      switch (kind) {
-        case SIMPLYP_V_Q:   sim = acc[0] * A * (1000.0 / 86400.0); break;
-        case SIMPLYP_V_SS:  sim = acc[1] * iq; break;
-        case SIMPLYP_V_TDP: sim = tdp; break;
-        case SIMPLYP_V_PP:  sim = pp; break;
-        case SIMPLYP_V_TP:  sim = tdp + pp; break;
-        default:            sim = tdp * f_TDP; break;
+      if (exact) {
+        switch (kind) {
+          case SIMPLYP_V_Q:   sim = acc[0] * A * 1000.0 / 86400.0; break;
+          case SIMPLYP_V_SS:  sim = (acc[1] / acc[0]) / A; break;
+          case SIMPLYP_V_TDP: sim = (acc[2] / acc[0]) / A; break;
+          case SIMPLYP_V_PP:  sim = (acc[3] / acc[0]) / A; break;
+          case SIMPLYP_V_TP:  sim = (acc[2] / acc[0]) / A + (acc[3] / acc[0]) / A; break;
+          default:            sim = ((acc[2] / acc[0]) / A) * f_TDP; break;
+        }
+      } else {
+        switch (kind) {
+          case SIMPLYP_V_Q:   sim = acc[0] * A * (1000.0 / 86400.0); break;
+          case SIMPLYP_V_SS:  sim = acc[1] * iq; break;
+          case SIMPLYP_V_TDP: sim = acc[2] * iq; break;
+          case SIMPLYP_V_PP:  sim = acc[3] * iq; break;
+          case SIMPLYP_V_TP:  sim = acc[2] * iq + acc[3] * iq; break;
+          default:            sim = acc[2] * iq * f_TDP; break;
+        }
       }
       if (a.sim_obs != nullptr) a.sim_obs[((size_t)m * a.V + v) * a.D + day] = sim;
       const double* oc = a.obs_const + 8 * v;
@@ -1093,8 +1109,11 @@ int quad_minblocks(long long grid) {
   int dev = 0, n_sm = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (grid <= 2ll * n_sm + n_sm / 4) return 2;      // all (or all but the lightest few) blocks resident at 2 per SM
-  if (grid <= 3ll * n_sm + n_sm / 4) return 3;
-  return 4;
+  // Beyond that the 168-register build (3 blocks per SM, no spills).  The 128-register build (4 blocks per SM) spills
+  // in the step loop and is no faster at any size since the step loop shrank to 580 instructions (round 2, B200:
+  // 2x10^4 members 19.6 vs 20.9 ms, 4x10^4 35.1 vs 35.3, 1.6x10^5 131.7 vs 131.1); it stays reachable through
+  // SIMPLYP_QUAD_MINBLOCKS=4 for A/B runs.
+  return 3;
 }
 
 // Pilot + counting sort: fills a.perm (one sub-catchment, quad kernel).  3 small launches + the pilot.

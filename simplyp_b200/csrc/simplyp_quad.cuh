@@ -208,7 +208,7 @@ SP_HD void quad_rhs(const Q& q, const QuadCoef<Q>& c, const typename Q::T& yA, c
   const T u = q.bcast(yA, 3);
   const T rV = qrcp40(yB + c.rvOff);        // lane 3: 1/Vr to 40 bits (the integration tolerance is 1e-7)
   const T QsA = q.bcast(G, 0), QsS = q.bcast(G, 1), Qg = q.bcast(G, 2);
-  e = q.exp(qfma(c.eY, yA, c.eU * u));
+  e = q.exp(qfma(c.eU, u, c.eY * yA));      // (the product that does not wait for the broadcast is formed first)
   const T gsum = qfma(c.aG, Qg, qfma(c.aSA, QsA, qfma(c.aSS, QsS, c.a0)));   // ready before the exponential
   const T src0 = qfma(c.bSA, QsA, qfma(c.bSS, QsS, qfma(c.bG, Qg, c.b0)));
   const T mult = qfma(rV, c.mA, c.m0);
@@ -448,8 +448,8 @@ struct QuadCarry {
 //   void wait(int day);                          // block until forcing and upstream inputs of `day` exist
 //   void forcing(int day, double& P, double& E, double& doy, double& T_air);
 //   void upstream(int day, double (&us)[4]);
-//   void emit(int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
-//             const Cold& c);                    // called on the quad leader only
+//   void emit(const Q& q, int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
+//             const Cold& c);                    // called by every lane; the policy decides which lanes write what
 //   void publish(int day);                       // leader only
 //
 // The whole record of one (member, sub-catchment) item: replaces model.py:491-724 for it.
@@ -613,13 +613,11 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       // along that direction is never damped and would random-walk over a 30-year record, so the volume carried
       // into the next day is put back on the curve (the reported Vr is the integrated one).
       s.yB = q.pick(y[iMsus], y[iTDPr], y[iPPr], sp_exp((1.0 - h.bQ) * u_end) * sp_rcp(h.cR));
-      q.sync();
+      if (valid) io.emit(q, day, yraw, Vr, acc, non, c);     // every lane (the output row is stored by all four)
+      q.sync();                                   // the row is complete before the leader publishes the day
       if (q.leader()) {
         qm.c = c;
-        if (valid) {
-          io.emit(day, yraw, Vr, acc, non, c);
-          io.publish(day);
-        }
+        if (valid) io.publish(day);
       }
       q.sync();
     }
