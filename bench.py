@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--e2e-members", type=int, default=None,
                     help="configs 3 and 5: members of the end-to-end leg (default: as many as fit 48 GB of pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target time of each cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=24.0, help="sizes the cpu_baseline samples (about this many seconds of CPU work in total)")
     args = ap.parse_args()
     if args.members is None:
         args.members = {2: 10000, 3: 64, 4: 1000000, 5: 4}[args.config]
