@@ -137,6 +137,18 @@ SP_HD double sp_rcp(double x) {
 #endif
 }
 
+// a / b given rb = 1/b to (nearly) full precision: product, exact remainder by fma, one correction.  Branch-free and
+// call-free; equal to the IEEE quotient except in rare last-bit cases.
+SP_HD double sp_div(double a, double b, double rb) {
+#if defined(__CUDA_ARCH__)
+  const double q = a * rb;
+  return fma(fma(-b, q, a), rb, q);
+#else
+  (void)rb;
+  return a / b;
+#endif
+}
+
 // 1/x to ~40 bits (one Newton step on the 20-bit hardware seed): for the reciprocal INSIDE the RHS evaluation, whose
 // accuracy requirement is the integration tolerance (1e-7), not the last bit.
 SP_HD double sp_rcp40(double x) {

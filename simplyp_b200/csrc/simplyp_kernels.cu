@@ -277,12 +277,13 @@ struct RunIO : IOBase<ROUTED> {
     const int e0 = a.parent_offsets[s], n = a.parent_offsets[s + 1] - e0;
     const int n_max = __reduce_max_sync(0xffffffffu, n);       // warp-uniform trip count, see upstream_ready()
     const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    const double rA_this = sp_rcp(A_this);             // (A_up / A_this by sp_div: no division subroutine in the day loop)
     for (int k = 0; k < n_max; ++k) {
       if (k < n) {
         const int p = a.parent_ids[e0 + k];
         const double* row = a.out + (((size_t)m * a.S + p) * a.D + day) * SIMPLYP_NOUT;
         const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-        us[0] += __ldcg(row + SIMPLYP_O_QR) * (A_up / A_this);   // :525
+        us[0] += __ldcg(row + SIMPLYP_O_QR) * sp_div(A_up, A_this, rA_this);   // :525
         us[1] += __ldcg(row + SIMPLYP_O_MSUS_FLUX);
         us[2] += __ldcg(row + SIMPLYP_O_TDP_FLUX);
         us[3] += __ldcg(row + SIMPLYP_O_PP_FLUX);
@@ -294,6 +295,7 @@ struct RunIO : IOBase<ROUTED> {
   // store it together: lane l writes columns l, l+4, l+8, ... — each store instruction of the warp moves eight
   // contiguous 32-byte pieces (one per quad) instead of eight single doubles, 7 store instructions per day instead
   // of 25 by the leader alone.  The column a lane stores is chosen with selects, not by indexing a register array.
+  static constexpr bool kAllLanesEmit = true;
   template <class Q>
   __device__ __forceinline__ void emit(const Q& q, int day, const double (&y)[NL], double Vr, const double (&acc)[NA],
                                        const double (&non)[13], const Cold&) const {
@@ -332,34 +334,35 @@ struct CalIO : IOBase<ROUTED> {
     const int e0 = a.parent_offsets[s], n = a.parent_offsets[s + 1] - e0;
     const int n_max = __reduce_max_sync(0xffffffffu, n);       // warp-uniform trip count, see upstream_ready()
     const double A_this = scp_member[(size_t)s * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
+    const double rA_this = sp_rcp(A_this);             // (A_up / A_this by sp_div: no division subroutine in the day loop)
     for (int k = 0; k < n_max; ++k) {
       if (k < n) {
         const int p = a.parent_ids[e0 + k];
         const double* row = a.flux + (((size_t)m * a.S + p) * a.D + day) * 4;
         const double A_up = scp_member[(size_t)p * SIMPLYP_NP_SC + SIMPLYP_SC_A_CATCH];
-        us[0] += __ldcg(row + 0) * (A_up / A_this);
+        us[0] += __ldcg(row + 0) * sp_div(A_up, A_this, rA_this);
         us[1] += __ldcg(row + 1);
         us[2] += __ldcg(row + 2);
         us[3] += __ldcg(row + 3);
       }
     }
   }
+  static constexpr bool kAllLanesEmit = false;
   template <class Q>
-  __device__ __forceinline__ void emit(const Q& q, int day, const double (&)[NL], double, const double (&acc)[NA],
+  __device__ __forceinline__ void emit(const Q&, int day, const double (&)[NL], double, const double (&acc)[NA],
                                        const double (&)[13], const Cold& c) const {
-    if (!q.leader()) return;
     if (a.flux != nullptr) {
       double* row = a.flux + (((size_t)m * a.S + s) * a.D + day) * 4;
       row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = acc[3];
     }
-    // simulated counterparts of the observed series (model.py:784-793, :840-845): Q_cumecs = Qr*A*1000/86400,
-    // concentrations (flux/Qr)/A_catch.  With rank statistics they are formed in the reference's own order of
-    // operations with IEEE divisions: Spearman's r is sensitive to the last bit wherever simulated values tie
-    // (recession days at the groundwater floor; measured 2e-6 on 13,700 pairs).  Without them two reciprocals serve all
-    // series (last-bit differences mean 1e-16 in NSE and the likelihood; the divisions cost 2 % of the run time).
+    // simulated counterparts of the observed series in the reference's own order of operations (model.py:784-793,
+    // :840-845): Q_cumecs = Qr*A*1000/86400, concentrations (flux/Qr)/A_catch.  The quotients are formed by sp_div
+    // (reciprocal, product, one fma of the exact remainder: the IEEE quotient in all but rare last-bit cases) because
+    // Spearman's r is sensitive to the last bit wherever simulated values tie (recession days at the groundwater floor:
+    // 2e-6 on 13,700 pairs between two orders of evaluation).  A true IEEE division would bring its slow-path
+    // subroutine into the kernel: its mere presence, never executed, cost 2-3 % of the run time (A/B on one box).
     const double A = c.A_catch;
-    const bool exact = a.sim_obs != nullptr;
-    const double iq = exact ? 0.0 : sp_rcp(acc[0]) * sp_rcp(A);
+    const double rQ = sp_rcp(acc[0]), rA = sp_rcp(A);
     int slot = 0;
     for (int v = 0; v < a.V; ++v) {
       if (__ldg(a.obs_desc + 2 * v) != s) continue;
@@ -368,24 +371,13 @@ struct CalIO : IOBase<ROUTED> {
       if (o != o) continue;  // no observation that day
       const int kind = __ldg(a.obs_desc + 2 * v + 1);
       double sim;
-      if (exact) {
-        switch (kind) {
-          case SIMPLYP_V_Q:   sim = acc[0] * A * 1000.0 / 86400.0; break;
-          case SIMPLYP_V_SS:  sim = (acc[1] / acc[0]) / A; break;
-          case SIMPLYP_V_TDP: sim = (acc[2] / acc[0]) / A; break;
-          case SIMPLYP_V_PP:  sim = (acc[3] / acc[0]) / A; break;
-          case SIMPLYP_V_TP:  sim = (acc[2] / acc[0]) / A + (acc[3] / acc[0]) / A; break;
-          default:            sim = ((acc[2] / acc[0]) / A) * f_TDP; break;
-        }
-      } else {
-        switch (kind) {
-          case SIMPLYP_V_Q:   sim = acc[0] * A * (1000.0 / 86400.0); break;
-          case SIMPLYP_V_SS:  sim = acc[1] * iq; break;
-          case SIMPLYP_V_TDP: sim = acc[2] * iq; break;
-          case SIMPLYP_V_PP:  sim = acc[3] * iq; break;
-          case SIMPLYP_V_TP:  sim = acc[2] * iq + acc[3] * iq; break;
-          default:            sim = acc[2] * iq * f_TDP; break;
-        }
+      switch (kind) {
+        case SIMPLYP_V_Q:   sim = sp_div(acc[0] * A * 1000.0, 86400.0, 1.0 / 86400.0); break;
+        case SIMPLYP_V_SS:  sim = sp_div(sp_div(acc[1], acc[0], rQ), A, rA); break;
+        case SIMPLYP_V_TDP: sim = sp_div(sp_div(acc[2], acc[0], rQ), A, rA); break;
+        case SIMPLYP_V_PP:  sim = sp_div(sp_div(acc[3], acc[0], rQ), A, rA); break;
+        case SIMPLYP_V_TP:  sim = sp_div(sp_div(acc[2], acc[0], rQ), A, rA) + sp_div(sp_div(acc[3], acc[0], rQ), A, rA); break;
+        default:            sim = sp_div(sp_div(acc[2], acc[0], rQ), A, rA) * f_TDP; break;
       }
       if (a.sim_obs != nullptr) a.sim_obs[((size_t)m * a.V + v) * a.D + day] = sim;
       const double* oc = a.obs_const + 8 * v;
@@ -1109,11 +1101,11 @@ int quad_minblocks(long long grid) {
   int dev = 0, n_sm = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (grid <= 2ll * n_sm + n_sm / 4) return 2;      // all (or all but the lightest few) blocks resident at 2 per SM
-  // Beyond that the 168-register build (3 blocks per SM, no spills).  The 128-register build (4 blocks per SM) spills
-  // in the step loop and is no faster at any size since the step loop shrank to 580 instructions (round 2, B200:
-  // 2x10^4 members 19.6 vs 20.9 ms, 4x10^4 35.1 vs 35.3, 1.6x10^5 131.7 vs 131.1); it stays reachable through
-  // SIMPLYP_QUAD_MINBLOCKS=4 for A/B runs.
-  return 3;
+  // Beyond that the 168-register build (3 blocks per SM, no spills) up to about 4x10^4 members; the 128-register
+  // build (4 blocks per SM, 136 B of spills in the step loop) only where the machine is several waves deep.  Round 2,
+  // B200, 3 vs 4 blocks: 2x10^4 members 19.6 vs 20.9 ms, 4x10^4 35.1 vs 35.3, 1.6x10^5 131.7-132.0 vs 130.3-131.1.
+  if (grid <= 9ll * n_sm) return 3;
+  return 4;
 }
 
 // Pilot + counting sort: fills a.perm (one sub-catchment, quad kernel).  3 small launches + the pilot.

@@ -357,7 +357,7 @@ struct QuadLU {
 template <class Q>
 SP_HD void quad_factor(const Q& q, const QuadJac<Q>& J, double hh, QuadLU<Q>& F) {
   using T = typename Q::T;
-  const double d = 1.0 / (ros::GAM * hh);
+  const double d = sp_rcp(ros::GAM * hh);      // (sp_rcp, not '/': no division subroutine in the step loop)
   F.gh = ros::GAM * hh;
   const T a = d - J.dAA;
   // lane 3: [a, -jUV; -jB4, d]^-1 = 1/det [d, jUV; jB4, a]
@@ -398,7 +398,7 @@ SP_HD double quad_attempt_ros(const Q& q, const QuadCoef<Q>& c, const QuadState<
   using T = typename Q::T;
   QuadLU<Q> F;
   quad_factor(q, J, hh, F);
-  const double ih = 1.0 / hh;
+  const double ih = sp_rcp(hh);
   T g1A, g1B, g1C, g2A, g2B, g2C, g3A, g3B, g3C, g4A, g4B, g4C, fA, fB, fC, ee;
   quad_solve(q, J, F, s.k1A, s.k1B, s.a1, g1A, g1B, g1C);
   quad_rhs(q, c, qfma(A21, g1A, s.yA), qfma(A21, g1B, s.yB), fA, fB, fC, ee);
@@ -449,7 +449,8 @@ struct QuadCarry {
 //   void forcing(int day, double& P, double& E, double& doy, double& T_air);
 //   void upstream(int day, double (&us)[4]);
 //   void emit(const Q& q, int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
-//             const Cold& c);                    // called by every lane; the policy decides which lanes write what
+//             const Cold& c);                    // kAllLanesEmit: called by every lane, else by the leader only
+//   static constexpr bool kAllLanesEmit;
 //   void publish(int day);                       // leader only
 //
 // The whole record of one (member, sub-catchment) item: replaces model.py:491-724 for it.
@@ -613,11 +614,22 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       // along that direction is never damped and would random-walk over a 30-year record, so the volume carried
       // into the next day is put back on the curve (the reported Vr is the integrated one).
       s.yB = q.pick(y[iMsus], y[iTDPr], y[iPPr], sp_exp((1.0 - h.bQ) * u_end) * sp_rcp(h.cR));
-      if (valid) io.emit(q, day, yraw, Vr, acc, non, c);     // every lane (the output row is stored by all four)
-      q.sync();                                   // the row is complete before the leader publishes the day
-      if (q.leader()) {
-        qm.c = c;
-        if (valid) io.publish(day);
+      if (IO::kAllLanesEmit) {                     // full output: the row is stored by all four lanes of the quad
+        if (valid) io.emit(q, day, yraw, Vr, acc, non, c);
+        q.sync();                                 // the row is complete before the leader publishes the day
+        if (q.leader()) {
+          qm.c = c;
+          if (valid) io.publish(day);
+        }
+      } else {                                    // calibration: the leader alone updates the statistics
+        q.sync();
+        if (q.leader()) {
+          qm.c = c;
+          if (valid) {
+            io.emit(q, day, yraw, Vr, acc, non, c);
+            io.publish(day);
+          }
+        }
       }
       q.sync();
     }

@@ -41,6 +41,7 @@ struct HostIO {
   bool ready(int) const { return true; }
   void wait(int) const {}
   void publish(int) const {}
+  static constexpr bool kAllLanesEmit = false;
   template <class Q>      // quad program: every lane calls it; the host's four lanes are one call
   void emit(const Q&, int day, const double (&y)[NL], double Vr, const double (&acc)[NA], const double (&non)[13],
             const Cold& c) const { emit(day, y, Vr, acc, non, c); }
