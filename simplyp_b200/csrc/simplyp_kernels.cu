@@ -101,10 +101,11 @@ constexpr int COST_BUCKETS = 4096;
 // Placement plan (simplyp_plan.cuh): device-side bookkeeping of the claims, an int array in the workspace.
 constexpr int PLAN_MAX_SM = 1024;                  // %smid is folded into this range
 constexpr int PLAN_FIRST_NEXT = 0;
+constexpr int PLAN_SKIPS = 1;                      // blocks that left without a list (launches with more blocks than lists)
 constexpr int PLAN_SM_ARR = 16;                    // [PLAN_MAX_SM] blocks that have arrived on the SM
 constexpr int PLAN_SM_LIST = PLAN_SM_ARR + PLAN_MAX_SM;         // [PLAN_MAX_SM] 1 + first-list of the SM, -1: none
-constexpr int PLAN_CLAIMED = PLAN_SM_LIST + PLAN_MAX_SM;        // [2 * PLAN_MAX_SM] list taken?
-constexpr int PLAN_INTS = PLAN_CLAIMED + 2 * PLAN_MAX_SM;       // zeroed before every launch
+constexpr int PLAN_CLAIMED = PLAN_SM_LIST + PLAN_MAX_SM;        // [3 * PLAN_MAX_SM] list taken?
+constexpr int PLAN_INTS = PLAN_CLAIMED + 3 * PLAN_MAX_SM;       // zeroed before every launch
 
 // raw sums kept in stats[][][] while a calibration kernel runs (finalised in place at the end)
 enum { RS_N = 0, RS_SSE, RS_SSE_LOG, RS_LL, RS_S1, RS_S2, RS_SOS, RS_SABS };
@@ -454,16 +455,24 @@ __device__ int plan_claim(const KArgs& a) {
     if (t < nSM && atomicCAS(claimed + t, 0, 1) == 0) list = t;
     __threadfence();
     atomicExch(plan + PLAN_SM_LIST + smid, list >= 0 ? list + 1 : -1);
-  } else if (slot == 1) {
+  } else if (slot < a.shape.resident) {             // second (third) block on the SM: the list that belongs to the first
     int v = 0;
     const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(plan + PLAN_SM_LIST + smid) : "memory");
     } while (v == 0 && clock64() - t0 < (1ll << 20));
-    if (v > 0 && plan_list_head(a.shape, nSM + v - 1) >= 0 && atomicCAS(claimed + nSM + v - 1, 0, 1) == 0) list = nSM + v - 1;
+    const int cand = slot * nSM + v - 1;
+    if (v > 0 && plan_list_head(a.shape, cand) >= 0 && atomicCAS(claimed + cand, 0, 1) == 0) list = cand;
   }
-  for (int l = 2 * nSM - 1; list < 0 && l >= 0; --l)
-    if (plan_list_head(a.shape, l) >= 0 && atomicCAS(claimed + l, 0, 1) == 0) list = l;
+  if (list < 0) {
+    // no list of its own.  A launch with more blocks than lists (3 resident blocks per SM) lets that many blocks go;
+    // any further block — and every block of an exact launch — takes the last list still free, so that every list is
+    // claimed exactly once whatever the hardware does.
+    const int spare = a.shape.n_launch() - a.shape.n_lists();
+    if (spare > 0 && atomicAdd(plan + PLAN_SKIPS, 1) < spare) return -1;
+    for (int l = a.shape.resident * nSM - 1; list < 0 && l >= 0; --l)
+      if (plan_list_head(a.shape, l) >= 0 && atomicCAS(claimed + l, 0, 1) == 0) list = l;
+  }
   return list < 0 ? -1 : plan_list_head(a.shape, list);
 }
 
@@ -472,8 +481,8 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
   extern __shared__ __align__(16) double smem_cold[];
   __shared__ int s_vblock;
   __shared__ double s_exp2tab[EXP_TAB];
-  // the placement plan exists for the 2-blocks-per-SM build of an ensemble of one sub-catchment only
-  constexpr bool PLAN = (MINB == 2) && !STIFF;
+  // the placement plan exists for the 2- and 3-blocks-per-SM builds of an ensemble of one sub-catchment only
+  constexpr bool PLAN = (MINB == 2 || MINB == 3) && !STIFF;
   if (threadIdx.x < EXP_TAB) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
   int vblock = (int)blockIdx.x;
 #ifdef SP_TIMELINE
@@ -1100,7 +1109,7 @@ int quad_minblocks(long long grid) {
   if (const char* e = getenv("SIMPLYP_QUAD_MINBLOCKS")) { const int v = atoi(e); if (v >= 2 && v <= 4) return v; }
   int dev = 0, n_sm = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if (grid <= 2ll * n_sm + n_sm / 4) return 2;      // all (or all but the lightest few) blocks resident at 2 per SM
+  if (grid <= 2ll * n_sm) return 2;                 // every block resident at 2 per SM (184 registers)
   // Beyond that the 168-register build (3 blocks per SM, no spills) up to about 4x10^4 members; the 128-register
   // build (4 blocks per SM, 136 B of spills in the step loop) only where the machine is several waves deep.  Round 2,
   // B200, 3 vs 4 blocks: 2x10^4 members 19.6 vs 20.9 ms, 4x10^4 35.1 vs 35.3, 1.6x10^5 131.7-132.0 vs 130.3-131.1.
@@ -1145,14 +1154,19 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   else if (pilot_minb == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(p);
   else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(p);
   cost_scan_kernel<<<1, 1024, 0, st>>>(p.hist);
-  // latency-bound regime (2 blocks per SM, at most a quarter wave too many): planned placement, see PLAN_*
+  // latency-bound regime (every block resident at once: 2 per SM, or 3 on some SMs with the 168-register build):
+  // planned placement, see PLAN_*.  B200, round 2, planned / unplanned 3-blocks launch: 10^4 members 9.4 / 11.6 ms,
+  // 1.2x10^4 11.0 / 12.0, 1.4x10^4 12.0 / 12.5 (the chained 2-blocks plan of round 1: 10.8 / 12.5 / 13.4).
   MemberLayout lay = {0, 0, 0, 0};
   int dev = 0, n_sm = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const char* e_plan = getenv("SIMPLYP_SM_PLAN");
   PlanShape shape;
-  if (quad_minblocks(grid) == 2 && n_sm <= PLAN_MAX_SM && dims.n_members >= 2048 && !(e_plan && atoi(e_plan) == 0) &&
-      plan_shape(grid, n_sm, shape)) {
+  const int minb = quad_minblocks(grid);
+  int q_max = n_sm - 1;
+  if (const char* e = getenv("SIMPLYP_PLAN_QMAX")) q_max = atoi(e);       // A/B runs
+  if ((minb == 2 || (minb == 3 && grid <= 2ll * n_sm + q_max)) && n_sm <= PLAN_MAX_SM && dims.n_members >= 2048 &&
+      !(e_plan && atoi(e_plan) == 0) && plan_shape(grid, n_sm, shape, minb)) {
     int solo = dims.n_members / 400 / 4 * 4;         // one block in about twelve of the heavy blocks
     if (const char* e = getenv("SIMPLYP_SOLO_WARPS")) { const int v = atoi(e); if (v >= 0) solo = v; }
     lay = member_layout(shape, dims.n_members, solo);
@@ -1248,12 +1262,10 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const int rc = order_members_by_cost<MODE>(dims, opt, a, L, ws, st);
     if (rc) return rc;
     const int minb = quad_minblocks(grid);
-    if (minb == 2) {
-      // planned placement: one block per list (n_sm first-lists, n_p + q second-lists), all resident at once
-      const unsigned g = a.plan ? (unsigned)a.shape.n_lists() : (unsigned)grid;
-      simplyp_quad_kernel<MODE, 2, false><<<g, block, smem, st>>>(a);
-    }
-    else if (minb == 3) simplyp_quad_kernel<MODE, 3, false><<<(unsigned)grid, block, smem, st>>>(a);
+    // planned placement: the launch fills the resident slots (one block per list at 2 per SM, 3 n_sm blocks at 3 per SM)
+    const unsigned g = a.plan ? (unsigned)a.shape.n_launch() : (unsigned)grid;
+    if (minb == 2) simplyp_quad_kernel<MODE, 2, false><<<g, block, smem, st>>>(a);
+    else if (minb == 3) simplyp_quad_kernel<MODE, 3, false><<<g, block, smem, st>>>(a);
     else simplyp_quad_kernel<MODE, 4, false><<<(unsigned)grid, block, smem, st>>>(a);
     g_launches.fetch_add(1);
     SP_CUDA(cudaGetLastError());

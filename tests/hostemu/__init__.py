@@ -110,16 +110,17 @@ def run_quad_split(forcing, member_params, sc_params, parent_offsets, parent_ids
     return out, diag
 
 
-def plan(M, n_sm, solo):
-    """Placement plan arithmetic: (index_of_rank [M], list_of_block [B], pos_in_list [B], (nY, nP, Q, n_lists)) or None."""
+def plan(M, n_sm, solo, resident=2):
+    """Placement plan arithmetic: (index_of_rank [M], list_of_block [B], pos_in_list [B],
+    (nY, nP, Q, n_lists, n_launch, resident)) or None."""
     lib = load()
     B = (M + 31) // 32
     idx = np.zeros(M, dtype=np.int32)
     lst = np.zeros(B, dtype=np.int32)
     pos = np.zeros(B, dtype=np.int32)
-    shape = np.zeros(4, dtype=np.int32)
+    shape = np.zeros(6, dtype=np.int32)
     vp = C.c_void_p
-    rc = lib.hostemu_plan(C.c_int(M), C.c_int(n_sm), C.c_int(solo), idx.ctypes.data_as(vp), lst.ctypes.data_as(vp),
+    rc = lib.hostemu_plan(C.c_int(M), C.c_int(n_sm), C.c_int(solo), C.c_int(resident), idx.ctypes.data_as(vp), lst.ctypes.data_as(vp),
                           pos.ctypes.data_as(vp), shape.ctypes.data_as(vp))
     assert rc >= 0, "a virtual block is out of range or sits in two lists"
     return None if rc == 0 else (idx, lst, pos, tuple(int(x) for x in shape))

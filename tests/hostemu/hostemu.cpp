@@ -158,16 +158,17 @@ extern "C" int hostemu_run_quad_split(const SimplypDims* dims, const SimplypOpti
 
 // Placement plan arithmetic (simplyp_plan.cuh) for M members on n_sm SMs: item index of every cost rank, and for
 // every virtual block the list that runs it and its position in that list.  Returns 0 if the plan does not apply.
-extern "C" int hostemu_plan(int M, int n_sm, int solo, int* index_of_rank, int* list_of_block, int* pos_in_list,
-                            int* shape4) {
+extern "C" int hostemu_plan(int M, int n_sm, int solo, int resident, int* index_of_rank, int* list_of_block,
+                            int* pos_in_list, int* shape6) {
   PlanShape p;
   const long long B = ((long long)M + 31) / 32;
-  if (!plan_shape(B, n_sm, p)) return 0;
-  shape4[0] = p.nY; shape4[1] = p.nP; shape4[2] = p.Q; shape4[3] = p.n_lists();
+  if (!plan_shape(B, n_sm, p, resident)) return 0;
+  shape6[0] = p.nY; shape6[1] = p.nP; shape6[2] = p.Q; shape6[3] = p.n_lists(); shape6[4] = p.n_launch();
+  shape6[5] = p.resident;
   const MemberLayout L = member_layout(p, M, solo);
   for (int r = 0; r < M; ++r) index_of_rank[r] = member_layout_index(r, L);
   for (int b = 0; b < (int)B; ++b) { list_of_block[b] = -1; pos_in_list[b] = -1; }
-  for (int l = 0; l < 2 * n_sm; ++l) {
+  for (int l = 0; l < 3 * n_sm; ++l) {
     int pos = 0;
     for (int vb = plan_list_head(p, l); vb >= 0; vb = plan_list_next(p, vb), ++pos) {
       if (vb >= (int)B || list_of_block[vb] != -1) return -1;      // out of range or claimed twice

@@ -105,26 +105,41 @@ def test_record_continued_from_a_stored_midnight_state_is_bitwise_the_same():
         assert np.array_equal(got, want) and np.array_equal(dg2, dg), split
 
 
+@pytest.mark.parametrize("resident", [2, 3])
 @pytest.mark.parametrize("n_sm", [148, 132])
-def test_placement_plan_covers_every_member_and_block_once(n_sm):
+def test_placement_plan_covers_every_member_and_block_once(n_sm, resident):
     """Arithmetic of the planned placement (simplyp_plan.cuh): for every ensemble size in the planned range the member
-    layout is a permutation, every virtual block sits in exactly one list, only the Q overflow lists hold two blocks,
-    the launch has one block per list, and the heaviest block's partner is the lightest of the partner region."""
+    layout is a permutation and every virtual block sits in exactly one list.  2 resident blocks per SM: only the Q
+    overflow lists hold two blocks and the launch has one block per list.  3 resident blocks per SM: no list holds two
+    blocks, the launch has 3 n_sm blocks, and the Q SMs of the light blocks have a first-, second- and third-list.  The
+    heaviest block's partner is the lightest of the partner region."""
     for M in (32 * n_sm + 1, 4800, 6001, 32 * 2 * n_sm - 7, 32 * 2 * n_sm, 32 * 2 * n_sm + 1, 9500, 10000,
               32 * (2 * n_sm + n_sm // 4)):
         B = (M + 31) // 32
         for solo in (0, 24):
-            res = hostemu.plan(M, n_sm, solo)
+            res = hostemu.plan(M, n_sm, solo, resident)
             if B <= n_sm:
                 assert res is None
                 continue
-            idx, lst, pos, (nY, nP, Q, n_lists) = res
+            idx, lst, pos, (nY, nP, Q, n_lists, n_launch, res_used) = res
             assert np.array_equal(np.sort(idx), np.arange(M)), (M, solo)              # a permutation of the members
             assert Q == max(0, B - 2 * n_sm) and nY == n_sm - Q and nY + nP + 3 * Q == B
-            assert (lst >= 0).all() and len(np.unique(lst)) == n_lists == n_sm + nP + Q
-            counts = np.bincount(lst, minlength=2 * n_sm)
-            assert (counts[:nY] == 1).all() and (counts[nY:n_sm] == 2).all() and counts.max() <= 2
-            assert sorted(pos[lst == nY].tolist()) == ([0, 1] if Q else sorted(pos[lst == nY].tolist()))
+            assert res_used == (3 if (resident == 3 and Q > 0) else 2)
+            assert (lst >= 0).all() and len(np.unique(lst)) == n_lists
+            counts = np.bincount(lst, minlength=3 * n_sm)
+            if res_used == 2:
+                assert n_lists == n_launch == n_sm + nP + Q
+                assert (counts[:nY] == 1).all() and (counts[nY:n_sm] == 2).all() and counts.max() <= 2
+                assert sorted(pos[lst == nY].tolist()) == ([0, 1] if Q else sorted(pos[lst == nY].tolist()))
+            else:
+                assert n_lists == B and n_launch == 3 * n_sm and counts.max() == 1 and (pos == 0).all()
+                assert (counts[:n_sm] == 1).all() and (counts[n_sm + nY:2 * n_sm] == 1).all()
+                assert (counts[2 * n_sm:2 * n_sm + nY] == 0).all() and (counts[2 * n_sm + nY:] == 1).all()
+                # the three blocks of a light SM are the ones the chained plan puts into one slot and beside it
+                chain = hostemu.plan(M, n_sm, solo, 2)[1]
+                for x in range(Q):
+                    trio = sorted(int(np.where(lst == c * n_sm + nY + x)[0][0]) for c in range(3))
+                    assert trio == sorted(np.where((chain == nY + x) | (chain == n_sm + nY + x))[0].tolist())
             # rank 0 leads virtual block 0; its partner block (list n_sm + 0) holds the lightest ranks of the partner region
             assert idx[0] == 0
             partner_block = int(np.where(lst == n_sm)[0][0])
