@@ -47,22 +47,27 @@
 #define SP_TOL_GMAX 8.0       // ... up to this factor (see run_quad)
 #endif
 #ifndef SP_STIFF_RATE
-#define SP_STIFF_RATE 150.0   // reach rate constant Qr/((1-b_Q) Vr) per day above which a day is integrated by the
-                              // Rosenbrock path (the explicit pair needs more than ~50 attempts per day there, the
-                              // Rosenbrock path 45-55 whatever the rate); measured on configs 3/5: 300 -> 150 is
-                              // 14 % faster on config 5, equal on config 3
+#define SP_STIFF_RATE 80.0    // reach rate constant Qr/((1-b_Q) Vr) per day above which a day is integrated by the
+                              // Rosenbrock path: the explicit pair is stability-bound there (~rate/3.3 attempts per
+                              // day), the Rosenbrock path needs 25-40 whatever the rate since its error norm relaxes
+                              // the reach's own terms (SP_ROS_RATE0); round 1 switched at 150 per day (45-55 attempts)
 #endif
 #ifndef SP_ROS_TOL_SCALE
 #define SP_ROS_TOL_SCALE 30.0 // Kaps-Rentrop's 3rd-order estimate is conservative: at 30x the tolerance the flows of a
                               // stiff reach are still within 5e-7 of LSODA/BDF at 1e-10 and its end-of-day states
                               // within 3e-6 (tests/...::test_stiff_reach_*), the explicit pair's own level
 #endif
+#ifndef SP_ROS_RATE0
+#define SP_ROS_RATE0 80.0     // Rosenbrock days: the error terms of the reach and of what it carries (u, Vr, in-stream masses,
+#define SP_ROS_GMAX 30.0      // daily sums) are relaxed by rate/SP_ROS_RATE0, at most SP_ROS_GMAX-fold, except in the last
+#endif                        // step of the day (the end-of-day states are outputs); see run_quad
 #ifndef SP_ROS_W_SOIL
-#define SP_ROS_W_SOIL 1.0
+#define SP_ROS_W_SOIL 3.0     // ... while the soil volumes and the groundwater are held 3x tighter than the Rosenbrock
+#define SP_ROS_W_VG 3.0       // tolerance scale alone would (a stiff reach does not make its land phase stiff)
 #endif
-#ifndef SP_ROS_W_VG
-#define SP_ROS_W_VG 1.0
-#endif
+#ifndef SP_H0_STIFF_C
+#define SP_H0_STIFF_C 0.15    // first step of a Rosenbrock day <= this / rate: the boundary layer the midnight jump of the
+#endif                        // forcing excites is ~1/rate wide (saves the 5-6 rejections that found this step size)
 #ifndef SP_W_B
 #define SP_W_B 1.0     // weight of the slot-B (in-stream masses, Vr) terms of the error norm
 #define SP_W_ACC 1.0   // weight of the daily accumulators
@@ -538,15 +543,12 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     // 1/rate at a fixed tolerance.  The tolerance therefore grows in proportion to the rate above SP_TOL_RATE0 per
     // day (at most SP_TOL_GMAX-fold): the same worst error against the oracle, 11 % fewer attempts on average and
     // 20 % fewer for the members with the fastest reaches, which are the longest chains of a launch.
-    double tol_inv2;
+    double tol_inv2, day_rate;
     {
       const double rate = 0.0 - q.first(q.bcast(J.dAA, 3));
+      day_rate = rate;
       double g = sp_min(sp_max(rate * (1.0 / SP_TOL_RATE0), 1.0), SP_TOL_GMAX);
-#ifdef SP_ROS_RATE0
       if (stiff) g = sp_min(sp_max(rate * (1.0 / SP_ROS_RATE0), 1.0), SP_ROS_GMAX);
-#else
-      if (stiff) g = 1.0;
-#endif
       tol_inv2 = stiff ? sp_rcp(g) : sp_rcp(g * g);        // stiff days: weight of the fast terms inside the norm
     }
     bool jac_fresh = true;
@@ -555,6 +557,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
     bool grow_ok = true;
     bool active = true;
     hstep = sp_min(hstep * SP_DAYSTART_FAC, T1);  // the forcing jumps at midnight
+    if (stiff) hstep = sp_min(hstep, SP_H0_STIFF_C * sp_rcp(day_rate));
 
     // ---- step loop: lock-step over the quads of a warp ------------------------------------------
     while (q.any(active)) {
