@@ -93,6 +93,12 @@ struct KArgs {
   int day_end;                  // one past the last day this launch integrates (D, or the pilot's days); D stays the
                                 // length of the record, i.e. the stride of forcing / obs / out
   int pilot_pass;               // 1: this launch is the pilot (writes cost / hist / carry, no diagnostics, no finalise)
+  // Networks: the record is cut into epochs of epoch_days days and the launch sweeps (epoch, block of items) units in
+  // epoch-major ticket order, the midnight state of every item crossing an epoch boundary through `carry` (indexed
+  // [m][s]): the chains of the main-stem reaches of epoch e then run beside the headwaters of epoch e+1 instead of
+  // alone at the end of the launch.  0 = one epoch.
+  int epoch_days, n_epochs;
+  int* epoch_done;              // [M][S] epochs an item has completed (release/acquire, like `progress`)
   int* plan;                    // placement of a cost-ordered ensemble on the SMs (PLAN_* below), or null
   PlanShape shape;              // valid when plan != nullptr
 };
@@ -132,6 +138,11 @@ struct ForcingRing {
   int end_day;                           // one past the last day this launch reads: no tile at or beyond it is fetched
 };
 
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
@@ -479,12 +490,13 @@ __device__ int plan_claim(const KArgs& a) {
 template <int MODE, int MINB, bool STIFF>
 __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) {
   extern __shared__ __align__(16) double smem_cold[];
-  __shared__ int s_vblock;
+  __shared__ int s_vblock, s_epoch;
   __shared__ double s_exp2tab[EXP_TAB];
   // the placement plan exists for the 2- and 3-blocks-per-SM builds of an ensemble of one sub-catchment only
   constexpr bool PLAN = (MINB == 2 || MINB == 3) && !STIFF;
   if (threadIdx.x < EXP_TAB) s_exp2tab[threadIdx.x] = kExp2Tab[threadIdx.x];
   int vblock = (int)blockIdx.x;
+  int epoch = 0, day_begin = a.day_begin, day_end = a.day_end;    // (per block in an epoch sweep of a network)
 #ifdef SP_TIMELINE
   unsigned long long sp_timeline_t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sp_timeline_t0));
@@ -495,9 +507,29 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     vblock = s_vblock;
     if (vblock < 0) return;
   } else if (STIFF && a.ticket != nullptr) {
-    if (threadIdx.x == 0) s_vblock = (int)atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
+    if (threadIdx.x == 0) {
+      unsigned unit = atomicAdd(reinterpret_cast<unsigned*>(a.ticket), 1u);
+      unsigned ep = 0;
+      if (a.n_epochs > 1) {                         // units in epoch-major order; the item count is device-side
+        // (blocks of 128 threads = 32 quads: a shift, not a 64-bit division — its subroutine's divergent slow path
+        // costs the step loop its convergence proof, see IOBase)
+        const unsigned n_vb = (unsigned)((a.level_item_off[a.n_levels] + 31) >> 5);
+        ep = unit / n_vb;
+        unit -= ep * n_vb;
+      }
+      s_vblock = (int)unit;
+      s_epoch = (int)ep;
+    }
     __syncthreads();
     vblock = s_vblock;
+    if (a.n_epochs > 1) {
+      // (through a warp reduction: its result is provably warp-uniform, a value read from shared memory is not — and
+      // the hand-over branches of run_quad, which hold quad shuffles, depend on it; see IOBase on convergence)
+      epoch = __reduce_max_sync(0xffffffffu, s_epoch);
+      if (epoch >= a.n_epochs) return;
+      day_begin = epoch * a.epoch_days;
+      day_end = day_begin + a.epoch_days < a.day_end ? day_begin + a.epoch_days : a.day_end;
+    }
   }
   const int quads_per_block = blockDim.x >> 2;
   QuadMem* qmem = reinterpret_cast<QuadMem*>(smem_cold);
@@ -514,12 +546,12 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     }
     if (threadIdx.x == 0) {
       ring->n_consumers = (unsigned)n_warps;        // the warps of the block that integrate something
-      ring->first_tile = a.day_begin / FORC_TILE;
-      ring->end_day = a.day_end;
+      ring->first_tile = day_begin / FORC_TILE;
+      ring->end_day = day_end;
       for (int i = 0; i < FORC_SLOTS; ++i) { mbar_init(&ring->full[i], 1); ring->left[i] = 0; }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       for (int i = 0; i < FORC_SLOTS; ++i)
-        if ((ring->first_tile + i) * FORC_TILE < a.day_end) tma_load_tile(ring, i, a.forcing, ring->first_tile + i, a.D);
+        if ((ring->first_tile + i) * FORC_TILE < day_end) tma_load_tile(ring, i, a.forcing, ring->first_tile + i, a.D);
     }
     __syncthreads();
     if ((int)(threadIdx.x >> 5) >= n_warps) return;  // (network launches have no further block-wide barrier)
@@ -568,14 +600,33 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     const int nc_last = fNCA_last > 0.0 ? 1 : (spl[SIMPLYP_SC_F_NC_S] > 0.0 ? 2 : 0);
 
     // calibration: shared-memory accumulators of the fit statistics, behind the forcing ring
-    const bool resume = a.carry != nullptr && !a.pilot_pass;
-    const QuadCarry* cin = resume ? a.carry + m : nullptr;
-    QuadCarry* cout = a.pilot_pass ? a.carry + m : nullptr;
+    // hand-over of the midnight state: pilot -> main launch of an ensemble (indexed by member), epoch -> epoch of a
+    // network sweep (indexed by item)
+    const bool sweep = STIFF && a.n_epochs > 1;
+    const size_t ci = sweep ? (size_t)m * a.S + s : (size_t)m;
+    const bool resume = sweep ? __any_sync(0xffffffffu, epoch > 0) : (a.carry != nullptr && !a.pilot_pass);
+    const bool hand_over = sweep ? __any_sync(0xffffffffu, epoch + 1 < a.n_epochs) : a.pilot_pass != 0;
+    const QuadCarry* cin = resume ? a.carry + ci : nullptr;
+    QuadCarry* cout = hand_over ? a.carry + ci : nullptr;
+    int sweep_status = 0;
+    if (sweep) {                                       // the item's previous epoch (an earlier ticket) has stored its state?
+      // (same shape as IOBase::wait: every condition a warp vote, so that the warp is provably converged afterwards)
+      const long long t0 = clock64();
+      const int* flag = a.epoch_done + ci;
+      bool ok = true;
+      unsigned ns = 64;
+      while (ok && !__all_sync(0xffffffffu, ld_acquire_s32(flag) >= epoch)) {
+        __nanosleep(ns);
+        if (ns < 4096) ns *= 2;
+        ok = __all_sync(0xffffffffu, (clock64() - t0) < (1ll << 37));
+      }
+      if (!ok) sweep_status = 4;
+    }
     double* sacc = nullptr;
     if (MODE == MODE_CAL) {
       sacc = reinterpret_cast<double*>(ring + 1) + (size_t)(threadIdx.x >> 2) * STAT_STRIDE;
       if ((threadIdx.x & 3) == 0) {
-        const double* src = resume ? a.carry_stats + (size_t)m * (STAT_SLOTS * 8) : nullptr;
+        const double* src = resume ? a.carry_stats + ci * (STAT_SLOTS * 8) : nullptr;
         for (int i = 0; i < STAT_SLOTS * 8; ++i) sacc[i] = src ? src[i] : 0.0;
       }
       __syncwarp();
@@ -587,10 +638,10 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
     ThreadCounters cnt;
     if (MODE == MODE_CAL) {
       CalIO<STIFF> io(a, m, s, ring, mp[SIMPLYP_P_F_TDP], sacc);
-      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, day_end, valid, qm, io, cnt, day_begin, cin, cout, resume, hand_over);
       if (valid && q.ql == 0) {
-        if (a.pilot_pass) {
-          double* dst = a.carry_stats + (size_t)m * (STAT_SLOTS * 8);
+        if (hand_over) {
+          double* dst = a.carry_stats + ci * (STAT_SLOTS * 8);
           for (int i = 0; i < STAT_SLOTS * 8; ++i) dst[i] = sacc[i];
         } else {
           io.finalise();
@@ -599,8 +650,19 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
       cnt.status |= io.wait_status;
     } else {
       RunIO<STIFF> io(a, m, s, ring);
-      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, a.day_end, valid, qm, io, cnt, a.day_begin, cin, cout);
+      run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, a.topt, day_end, valid, qm, io, cnt, day_begin, cin, cout, resume, hand_over);
       cnt.status |= io.wait_status;
+    }
+    if (sweep) {
+      cnt.status |= sweep_status;
+      if (hand_over) {                                 // state (and statistic sums) stored by this thread: publish the epoch
+        if (valid && q.ql == 0) {
+          // a status bit raised in this epoch travels with the state (run_quad stored its own before the waits' bits)
+          if (cnt.status) a.carry[ci].status |= (int)cnt.status;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.epoch_done + ci), "r"(epoch + 1) : "memory");
+        }
+        return;
+      }
     }
     if (a.pilot_pass) {                                // the pilot's product: the cost of every member
       if (valid && q.ql == 0) {
@@ -1015,7 +1077,8 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
   size_t off_po, off_pid, off_bylevel, off_lvlstart, off_topo_end, off_order, off_area, off_lvl_items, off_lvl_order, off_oc,
-      off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket, off_progress, off_flux, off_obs_log,
+      off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket, off_progress, off_epoch_done, off_flux,
+      off_obs_log,
       off_obs_rank, off_sim_obs, total;
 };
 
@@ -1037,12 +1100,16 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   L.off_hist = o;  o = align_up(o + sizeof(unsigned) * COST_BUCKETS);
   L.off_perm = o;  o = align_up(o + sizeof(int) * (size_t)d.n_members);
   L.off_plan = o;  if (d.n_sc == 1) o = align_up(o + sizeof(int) * (size_t)PLAN_INTS);
+  // midnight states handed over between launches (ensemble: pilot -> main, per member) or epochs (network: per item)
+  const size_t n_carry = d.n_sc == 1 ? (d.n_members >= 512 ? (size_t)d.n_members : 0) : (size_t)d.n_members * d.n_sc;
   L.off_carry = o;
-  if (d.n_sc == 1 && d.n_members >= 512) o = align_up(o + sizeof(QuadCarry) * (size_t)d.n_members);
+  o = align_up(o + sizeof(QuadCarry) * n_carry);
   L.off_carry_stats = o;
-  if (d.n_sc == 1 && d.n_members >= 512 && cal) o = align_up(o + sizeof(double) * STAT_SLOTS * 8 * (size_t)d.n_members);
+  if (cal) o = align_up(o + sizeof(double) * STAT_SLOTS * 8 * n_carry);
   L.off_ticket = o; o = align_up(o + sizeof(int));
   L.off_progress = o;
+  if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
+  L.off_epoch_done = o;
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
   L.off_flux = o;
   if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
@@ -1314,7 +1381,24 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     const long long n = (long long)(i_ls[l + 1] - i_ls[l]) * dims.n_members;
     bound += (n + 7) / 8 * 8 + ((dims.n_members % 8 != 0 && i_ls[l + 1] - i_ls[l] > 1) ? 8 : 0);
   }
-  const long long grid = (bound + qpb - 1) / qpb;
+  long long grid = (bound + qpb - 1) / qpb;
+  // Epoch sweep (KArgs::epoch_days): a whole number of forcing tiles per epoch.  Without it the launch is the bulk of
+  // the headwaters followed by the chains of the main-stem reaches at low occupancy.  An epoch should be long against
+  // the depth of the network (the wavefront needs one day-time per level to reach the outlet): four days per level,
+  // at least 256.  B200, round 2, one piece / 256 / 512 / 1024 / 2048 days per epoch: config 3 (32 levels) at 64
+  // members 767 / 555 / 564 / 567 / 583 ms, at 256 members 2185 / 1922 / 1920 / 1932 / 1929; config 5 (487 levels) at
+  // 8 members 2565 / 2788 / 2550 / 2411 / 2348 ms, at 1 member 1339 / 1297 / 1244 / 1253 / 1279.
+  int epoch_days = (4 * nl + FORC_TILE - 1) / FORC_TILE * FORC_TILE;
+  if (epoch_days < 2 * FORC_TILE) epoch_days = 2 * FORC_TILE;
+  if (const char* e = getenv("SIMPLYP_EPOCH_DAYS")) epoch_days = atoi(e) / FORC_TILE * FORC_TILE;   // 0: off (A/B runs)
+  if (epoch_days > 0 && dims.n_days > epoch_days && grid * ((dims.n_days + epoch_days - 1) / epoch_days) < (1ll << 30)) {
+    a.epoch_days = epoch_days;
+    a.n_epochs = (dims.n_days + epoch_days - 1) / epoch_days;
+    a.epoch_done = reinterpret_cast<int*>(ws + L.off_epoch_done);
+    a.carry = reinterpret_cast<QuadCarry*>(ws + L.off_carry);
+    a.carry_stats = reinterpret_cast<double*>(ws + L.off_carry_stats);
+    grid *= a.n_epochs;
+  }
   // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of the
   // 2-blocks-per-SM variant
   simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);

@@ -482,7 +482,10 @@ struct QuadCarry {
 template <bool STIFF, class Q, class IO>
 SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0, int nc_last,
                     const ThreadOptions& opt, int n_days, bool valid, QuadMem& qm, IO& io, ThreadCounters& cnt,
-                    int day_begin = 0, const QuadCarry* carry_in = nullptr, QuadCarry* carry_out = nullptr) {
+                    int day_begin, const QuadCarry* carry_in, QuadCarry* carry_out, bool resume, bool hand_over) {
+  // resume / hand_over say whether carry_in / carry_out are used.  They are separate arguments because the branches they
+  // guard hold quad shuffles and barriers: the caller passes conditions that are provably warp-uniform (a kernel
+  // parameter, a warp vote), which a comparison of the per-thread pointers with null is not.
   using T = typename Q::T;
   QuadCoef<Q> qc;
   QuadState<Q> s;
@@ -505,7 +508,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   double snow_depth = mp[SIMPLYP_P_D_SNOW_0];       // only used with snow_on_device
   const double T1 = opt.step_len;
   double hstep = 0.05 * T1;
-  if (carry_in != nullptr) {                        // continue a record: everything that crosses midnight
+  if (resume) {                                     // continue a record: everything that crosses midnight
     s.yA = q.pick(carry_in->yA[0], carry_in->yA[1], carry_in->yA[2], carry_in->yA[3]);
     s.yB = q.pick(carry_in->yB[0], carry_in->yB[1], carry_in->yB[2], carry_in->yB[3]);
     hstep = carry_in->hstep;
@@ -675,7 +678,7 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
       q.sync();
     }
   }
-  if (carry_out != nullptr) {
+  if (hand_over) {
     const double a0 = q.first(q.bcast(s.yA, 0)), a1 = q.first(q.bcast(s.yA, 1)), a2 = q.first(q.bcast(s.yA, 2)),
                  a3 = q.first(q.bcast(s.yA, 3));
     const double b0 = q.first(q.bcast(s.yB, 0)), b1 = q.first(q.bcast(s.yB, 1)), b2 = q.first(q.bcast(s.yB, 2)),
@@ -697,6 +700,16 @@ SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0
   cnt.rhs_evals = n_rhs;
   cnt.status = status;
   (void)Kf;
+}
+
+
+// The whole record, or a part of it continued from / handed over to a stored midnight state (host builds, tests).
+template <bool STIFF, class Q, class IO>
+SP_HD void run_quad(const Q& q, const double* mp, const double* sp, double A_qr0, int nc_last,
+                    const ThreadOptions& opt, int n_days, bool valid, QuadMem& qm, IO& io, ThreadCounters& cnt,
+                    int day_begin = 0, const QuadCarry* carry_in = nullptr, QuadCarry* carry_out = nullptr) {
+  run_quad<STIFF>(q, mp, sp, A_qr0, nc_last, opt, n_days, valid, qm, io, cnt, day_begin, carry_in, carry_out,
+                  carry_in != nullptr, carry_out != nullptr);
 }
 
 }  // namespace simplyp

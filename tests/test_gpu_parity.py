@@ -201,6 +201,39 @@ def test_network_ensemble_lanes_share_a_warp(cabi):
     assert np.allclose(nse, st[:, 0, 1], rtol=1e-10, atol=1e-10)
 
 
+def test_epoch_sweep_is_invisible_in_the_results(cabi, monkeypatch):
+    """Networks are swept in epochs (units of >= 256 days x a block of items, epoch-major, the midnight state of every item
+    handed over through the workspace) so that the main-stem chains of one epoch run beside the headwaters of the next.
+    The hand-over is exact: 64 reaches x 3 members x 700 days in epochs of 128 days (6 epochs), 256 days (the default, 3)
+    and in one piece give the same bits — full output, diagnostics, and the fused statistics of a calibration run."""
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, synthetic, tarland
+    p_SU, dyn, p, p_LU, p_SC0, p_struc0, met, obs = tarland.load("2003-06-01", "2005-04-30", dynamic="y")
+    assert len(met) == 700
+    p, p_SC, p_struc = synthetic.random_network(p, p_SC0[1], n_sc=64, seed=3)
+    pk.validate_land_use(p_SC, p["SC_list"])
+    topo = pk.build_topology(p_struc, p["SC_list"])
+    opt = spm.make_options(p_SU, p, dyn, topo)
+    samples = ens.latin_hypercube(3, seed=5)
+    member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+    forcing = pk.forcing_matrix(met)
+    outlet = topo.sc_ids[-1]
+    obs_m, desc, labels = pk.obs_arrays({outlet: obs[1]}, topo, met.index, ("Q", "TDP"))
+    res = {}
+    for days in ("0", "128", None):
+        if days is None:
+            monkeypatch.delenv("SIMPLYP_EPOCH_DAYS", raising=False)
+        else:
+            monkeypatch.setenv("SIMPLYP_EPOCH_DAYS", days)
+        out, dg = cabi.run_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, opt)
+        st, dgc = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
+        assert not np.any(dg[..., 3]) and not np.any(dgc[..., 3]) and np.all(np.isfinite(out))
+        res[days] = (out, dg, st, dgc)
+    for days in ("128", None):
+        for a, b in zip(res["0"], res[days]):
+            assert np.array_equal(a, b, equal_nan=True), days
+    assert res["0"][1][..., 0].min() > 700 * 3
+
+
 def test_long_record_wraps_the_forcing_ring(cabi):
     """1,300 days = 11 forcing tiles through the 4-slot TMA ring (slots are re-armed and refilled), with
     members of very different speed in one block; member 0 is checked against the oracle over the whole window."""
