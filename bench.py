@@ -15,7 +15,7 @@ per second, whole job.  Workloads = BASELINE.json `configs`:
                         --members parameter sets per GPU (default 64), full daily output kept in HBM;
                         e2e = simplyp_run_host on a member subset whose output fits pinned host memory.
   --config 5            synthetic 4096-sub-catchment x 3 land-use network, 50-year daily run, full daily output written
-                        to HBM (200 B per member-SC-day), --members per GPU (default 4).
+                        to HBM (200 B per member-SC-day), --members per GPU (default 8).
 
 Members are sharded over ranks with no data-path collective; the only collective is the all-gather of the per-member
 statistics (configs 2 and 4).  Prints ONE JSON line (rank 0).  See DESIGN.md §5 for how each field is obtained.
@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--members", type=int, default=None,
-                    help="members per GPU (configs 2, 3, 5; defaults 10000 / 64 / 4) or in total (config 4; 10^6)")
+                    help="members per GPU (configs 2, 3, 5; defaults 10000 / 64 / 8) or in total (config 4; 10^6)")
     ap.add_argument("--period", default="2004", choices=["2004", "full"], help="configs 2 and 4: Tarland period")
     ap.add_argument("--rtol", type=float, default=None)
     ap.add_argument("--atol", type=float, default=None)
@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=24.0, help="sizes the cpu_baseline samples (about this many seconds of CPU work in total)")
     args = ap.parse_args()
     if args.members is None:
-        args.members = {2: 10000, 3: 64, 4: 1000000, 5: 4}[args.config]
+        args.members = {2: 10000, 3: 64, 4: 1000000, 5: 8}[args.config]
     return args
 
 

@@ -1,5 +1,7 @@
-"""Experiment: epoch length of the network sweep (SIMPLYP_EPOCH_DAYS; 0 = one piece) on BASELINE configs 3 and 5.
-    python scripts/exp_epochs.py 3:64 5:8 -- 0 256 512 1024"""
+"""Experiment: epoch length of the network sweep (SIMPLYP_EPOCH_DAYS; 0 = one piece) — or any other environment
+switch of the library, given as KEY=VALUE — on BASELINE configs 3 and 5.
+    python scripts/exp_epochs.py 3:64 5:8 -- 0 256 512 1024
+    python scripts/exp_epochs.py 3:64 5:8 -- SIMPLYP_NET_MINBLOCKS=2 SIMPLYP_NET_MINBLOCKS=3"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,7 +24,10 @@ for cfg, M in cases:
     po, pid = topo.parent_offsets, topo.parent_ids
     ref = None
     for E in lengths:
-        os.environ["SIMPLYP_EPOCH_DAYS"] = E
+        if "=" in E:
+            os.environ[E.split("=")[0]] = E.split("=")[1]
+        else:
+            os.environ["SIMPLYP_EPOCH_DAYS"] = E
         eng.run(d_f, d_m, d_s, po, pid, opt, out=out, diag=diag)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,7 +39,7 @@ for cfg, M in cases:
         chk = (float(out[:, :, ::97, 5].sum().item()), int(diag[..., 0].sum().item()), int(diag[..., 3].max().item()))
         same = "" if ref is None else (" same checksum" if chk == ref else " DIFFERENT %r vs %r" % (chk, ref))
         ref = ref or chk
-        print("config %d, %d members, epoch %5s days: %8.1f ms  %.3e member-SC-days/s  status %d%s"
+        print("config %d, %d members, setting %-26s: %8.1f ms  %.3e member-SC-days/s  status %d%s"
               % (cfg, M, E, ms, M * S * D / (ms * 1e-3), chk[2], same), flush=True)
     del out
     torch.cuda.empty_cache()

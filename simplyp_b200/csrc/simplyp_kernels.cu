@@ -1234,7 +1234,8 @@ int order_members_by_cost(const SimplypDims& dims, const SimplypOptions& opt, KA
   if (const char* e = getenv("SIMPLYP_PLAN_QMAX")) q_max = atoi(e);       // A/B runs
   if ((minb == 2 || (minb == 3 && grid <= 2ll * n_sm + q_max)) && n_sm <= PLAN_MAX_SM && dims.n_members >= 2048 &&
       !(e_plan && atoi(e_plan) == 0) && plan_shape(grid, n_sm, shape, minb)) {
-    int solo = dims.n_members / 400 / 4 * 4;         // one block in about twelve of the heavy blocks
+    int solo = dims.n_members / 100 / 4 * 4;         // about one warp in five of the heavy blocks (10^4 members:
+                                                     // 0 / 24 / 96 / 240 led warps 9.55 / 9.42 / 9.35 / 9.51 ms)
     if (const char* e = getenv("SIMPLYP_SOLO_WARPS")) { const int v = atoi(e); if (v >= 0) solo = v; }
     lay = member_layout(shape, dims.n_members, solo);
     int* plan = reinterpret_cast<int*>(ws + L.off_plan);
@@ -1382,6 +1383,7 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     bound += (n + 7) / 8 * 8 + ((dims.n_members % 8 != 0 && i_ls[l + 1] - i_ls[l] > 1) ? 8 : 0);
   }
   long long grid = (bound + qpb - 1) / qpb;
+  const long long grid_one_epoch = grid;
   // Epoch sweep (KArgs::epoch_days): a whole number of forcing tiles per epoch.  Without it the launch is the bulk of
   // the headwaters followed by the chains of the main-stem reaches at low occupancy.  An epoch should be long against
   // the depth of the network (the wavefront needs one day-time per level to reach the outlet): four days per level,
@@ -1399,9 +1401,20 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     a.carry_stats = reinterpret_cast<double*>(ws + L.off_carry_stats);
     grid *= a.n_epochs;
   }
-  // networks get the build with the Rosenbrock path for stiff (main-stem) reaches; it needs the registers of the
-  // 2-blocks-per-SM variant
-  simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
+  // Networks get the build with the Rosenbrock path for stiff (main-stem) reaches.  Its 2-blocks-per-SM variant (226
+  // registers) serves launches that the chains of the main stem bound; when the items of one epoch fill the machine
+  // several times over, the 3-blocks variant (168 registers, 40 B of spills) is faster.  B200, round 2, 2 / 3 blocks:
+  // config 3 at 64 members (512 blocks per epoch) 557 / 666 ms, at 256 members (2048) 1921 / 1739; config 5 at 8
+  // members (1024) 2346 / 2166, at 1 member (128) 1266 / 1583.
+  int net_minb = 2;
+  {
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (grid_one_epoch >= 6ll * n_sm) net_minb = 3;
+  }
+  if (const char* e = getenv("SIMPLYP_NET_MINBLOCKS")) { const int v = atoi(e); if (v == 2 || v == 3) net_minb = v; }
+  if (net_minb == 3) simplyp_quad_kernel<MODE, 3, true><<<(unsigned)grid, block, smem, st>>>(a);
+  else simplyp_quad_kernel<MODE, 2, true><<<(unsigned)grid, block, smem, st>>>(a);
   g_launches.fetch_add(2);
   SP_CUDA(cudaGetLastError());
   return SIMPLYP_OK;
