@@ -171,7 +171,8 @@ typedef struct SimplypDims {
 } SimplypDims;
 
 typedef struct SimplypOptions {
-  double  rtol;              /* relative tolerance of the embedded RK error control */
+  double  rtol;              /* relative tolerance of the embedded RK error control (of a day whose reach relaxes slowly:
+                                both tolerances grow with the reach's rate constant) */
   double  atol;              /* absolute tolerance (same for all 12 states, like odeint's scalar atol) */
   double  step_len;          /* length of one forcing step in days (reference default 1.0) */
   int32_t max_steps_per_day; /* step attempts allowed per day before the status bit is raised */

@@ -11,11 +11,12 @@ out = ["# Step loop (one lock-step Runge-Kutta attempt of a warp = 8 quads) of t
        "# 1385 for the network build.  Round 2: no BRA.DIV anywhere in the library (routing loops compile-time per build,",
        "# warp-uniform trip counts, votes instead of thread-varying conditions), six quad broadcasts per evaluation (76 SHFL),",
        "# exponent add on the high word, no division subroutine in any day loop."]
-for name, pat in (("<MODE_CAL, MINB=2, STIFF=false>  (headline: 10^4-member ensembles)", "kernelILi1ELi2ELb0"),
-                  ("<MODE_CAL, MINB=3, STIFF=false>  (ensembles up to 9 blocks per SM)", "kernelILi1ELi3ELb0"),
+for name, pat in (("<MODE_CAL, MINB=2, STIFF=false>  (ensembles of at most 2 blocks per SM: <= 9,472 members)", "kernelILi1ELi2ELb0"),
+                  ("<MODE_CAL, MINB=3, STIFF=false>  (headline: 10^4-member ensembles, 3 resident blocks on 17 SMs; up to 9 blocks per SM)", "kernelILi1ELi3ELb0"),
                   ("<MODE_CAL, MINB=4, STIFF=false>  (larger ensembles)", "kernelILi1ELi4ELb0"),
                   ("<MODE_RUN, MINB=2, STIFF=false>  (full output, one sub-catchment)", "kernelILi0ELi2ELb0"),
                   ("<MODE_RUN, MINB=2, STIFF=true>   (networks: explicit + Rosenbrock paths)", "kernelILi0ELi2ELb1"),
+                  ("<MODE_RUN, MINB=3, STIFF=true>   (networks whose epochs fill the machine six times over)", "kernelILi0ELi3ELb1"),
                   ("<MODE_CAL, MINB=2, STIFF=true>", "kernelILi1ELi2ELb1")):
     r = subprocess.run([sys.executable, mix, lib, pat], capture_output=True, text=True).stdout.strip().splitlines()
     out.append("\n## " + name)
@@ -24,8 +25,8 @@ sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=Tru
 out.append("\n## whole library: UBLKCP (cp.async.bulk) %d, SYNCS.ARRIVE.TRANS64 %d, SYNCS.PHASECHK %d, BRA.DIV %d, SHFL %d, STG %d"
            % (sass.count("UBLKCP"), sass.count("SYNCS.ARRIVE.TRANS64"), sass.count("SYNCS.PHASECHK"), sass.count("BRA.DIV"),
               sass.count("SHFL."), sass.count("STG.")))
-r = subprocess.run([sys.executable, mix, lib, "kernelILi1ELi2ELb0", "--dump"], capture_output=True, text=True).stdout.splitlines()
-out.append("\n## full listing of the step loop of <MODE_CAL, 2, false>")
+r = subprocess.run([sys.executable, mix, lib, "kernelILi1ELi3ELb0", "--dump"], capture_output=True, text=True).stdout.splitlines()
+out.append("\n## full listing of the step loop of <MODE_CAL, 3, false>")
 out += r[3:]
 open(os.path.join(ROOT, "profiles", "r02_step_loop.sass"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[7:30]))
