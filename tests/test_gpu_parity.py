@@ -547,12 +547,14 @@ def test_ensemble_container_equals_one_shot_run(cabi, tmp_path):
     assert np.array_equal(got, out[:, :, :, pk.RAW_COLS.index("TDP_kg/day")])
 
 
-@pytest.mark.parametrize("M", [4800, 6001, 9500, 10000])
+@pytest.mark.parametrize("M", [4800, 6001, 9500, 10000, 13999])
 def test_planned_placement_is_invisible_in_the_results(cabi, M, monkeypatch):
-    """Latency-bound ensembles (more blocks than SMs, at most a quarter wave beyond 2 blocks per SM) are placed on the
-    SMs by plan (claim by %smid, reversed partner blocks, warps led by one heavy member, chained light blocks): the
+    """Latency-bound ensembles (more blocks than SMs, fewer than 3 per SM) are placed on the SMs by plan (claim by
+    %smid, reversed partner blocks, warps led by one heavy member; beyond 2 blocks per SM the 168-register build with
+    three light blocks resident on some SMs and 3 x 148 blocks launched, of which the spare ones leave): the
     statistics and diagnostics of every member must be bit-identical to the plain launch.  Sizes: a few partner
-    blocks only (4800), a ragged last block (6001), one and seventeen blocks beyond the resident set (9500, 10000)."""
+    blocks only (4800), a ragged last block (6001), one, seventeen and 142 SMs with three blocks (9500, 10000, 13999:
+    the last one ragged as well)."""
     import torch
     import bench
     from simplyp_b200 import model as spm, packing as pk
