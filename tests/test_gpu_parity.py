@@ -449,7 +449,7 @@ def test_snow_parameters_in_the_ensemble(cabi):
 @pytest.mark.parametrize("area", [0.05, 5.0])
 def test_stiff_reach_vs_oracle(cabi, area):
     """The Rosenbrock path of the quad kernel (stiff main-stem-like reach) against LSODA/BDF at tight tolerance."""
-    per_day = parity.check_stiff_chain(cabi.run_host, area, max_steps_per_day=100)
+    per_day = parity.check_stiff_chain(cabi.run_host, area, max_steps_per_day=60)
     assert per_day > 20
 
 
