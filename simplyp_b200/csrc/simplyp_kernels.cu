@@ -447,9 +447,12 @@ struct CalIO : IOBase<ROUTED> {
 // ------------------------------------------------------------------------------------------ K1 (quad form)
 // One QUAD of lanes per (member, sub-catchment) item, 8 items per warp in day lock-step (simplyp_quad.cuh).
 // Shared memory: one QuadMem per quad, then the forcing ring.
-// MINB = resident blocks per SM the register allocation is made for: 4 (128 registers, 16 warps per SM) when the
-// ensemble fills the machine; 2 (206 registers: no spills, constants stay in registers, 10 % fewer
-// instructions per step) when there are too few warps for that anyway and single-warp latency is what counts.
+// MINB = resident blocks per SM the register allocation is made for (quad_minblocks): 2 (186 registers) for ensembles
+// of at most 2 blocks per SM, 3 (164 registers, no spills either) up to 9 blocks per SM — with the placement plan
+// below 3 blocks per SM — and 4 (128 registers, 16 warps per SM, ~150 B of spills) when the ensemble fills the machine
+// several times over.  Networks (STIFF): 2 (226 registers) or 3 (168 registers, 40 B of spills), see launch_levels.
+// A launch is either an ensemble of one sub-catchment (optionally the pilot or the continuation of one, optionally
+// planned) or a network (tickets in dispatch order, optionally swept in epochs: KArgs::epoch_days).
 enum { MODE_RUN = 0, MODE_CAL = 1 };
 // Thread 0 of a block claims a list (see the PLAN_* comment) and returns its first virtual block.
 __device__ int plan_claim(const KArgs& a) {
