@@ -356,14 +356,18 @@ def run_ours(args):
         gb = ens.GatherBuffers(M_total, (V, pk.NSTAT), eng.device)
         stats = gb.local
 
-        def step():
+        def step(mid=None):
             eng.calibrate(d_forc, d_mem, d_sc, po, pid, d_obs, d_desc, opt, stats=stats, diag=diag)
+            if mid is not None:
+                mid.record()               # this rank's own integration ends here; the all-gather waits for the slowest rank
             return gb.gather()
     else:
         out = torch.empty((M_local, S, D, pk.NOUT), dtype=torch.float64, device=eng.device)
 
-        def step():
+        def step(mid=None):
             eng.run(d_forc, d_mem, d_sc, po, pid, opt, out=out, diag=diag)
+            if mid is not None:
+                mid.record()
             return out
 
     def barrier():
@@ -383,12 +387,13 @@ def run_ours(args):
 
     launches0 = _cabi.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the events)
         ev[k][0].record()
-        step()
+        step(mid[k])
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -400,6 +405,14 @@ def run_ours(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
     value = M_total * S * D / (ms_per_step * 1e-3)
+    # every rank's OWN integration time per step (start of the step to the end of its kernels, before the all-gather):
+    # the ranks integrate different members, and a step lasts as long as the slowest of them
+    own_ms = torch.tensor([float(np.mean([a.elapsed_time(m) for (a, _b), m in zip(ev, mid)]))], dtype=torch.float64,
+                          device=eng.device)
+    ranks_own_ms = [own_ms.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ranks_own_ms, own_ms)
+    ranks_own_ms = [round(float(t.item()), 4) for t in ranks_own_ms]
 
     # ---- integrator work counters for the roofline (device-counted)
     dg = diag.sum(dim=(0, 1)).cpu().numpy().astype(float)
@@ -543,6 +556,7 @@ def run_ours(args):
                     "api": api, "members_per_gpu": M_e2e, "steps": e2e_reps, "matches_device_leg": same},
             "roofline": roofline,
             "clocks": clocks, "integrator_status_bits": status_any, "wall_s_timed_region": t_wall,
+            "ranks_own_ms_per_step": ranks_own_ms,
         }
         if not args.no_cpu_baseline and world == 1:
             try:

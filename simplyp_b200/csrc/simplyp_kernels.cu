@@ -18,11 +18,13 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "simplyp_quad.cuh"
@@ -99,6 +101,10 @@ struct KArgs {
   // alone at the end of the launch.  0 = one epoch.
   int epoch_days, n_epochs;
   int* epoch_done;              // [M][S] epochs an item has completed (release/acquire, like `progress`)
+  // *_host entry points stream the rows of a finished epoch to the caller's buffer while later epochs integrate: the
+  // last item to finish epoch e raises epoch_flags_host[e] (mapped pinned memory), which the host thread polls
+  unsigned* epoch_count;        // [n_epochs] items that have finished the epoch, or null
+  int* epoch_flags_host;        // [n_epochs] device pointer of the mapped flags, or null
   int* plan;                    // placement of a cost-ordered ensemble on the SMs (PLAN_* below), or null
   PlanShape shape;              // valid when plan != nullptr
 };
@@ -663,6 +669,13 @@ __global__ void __launch_bounds__(128, MINB) simplyp_quad_kernel(const KArgs a) 
           // a status bit raised in this epoch travels with the state (run_quad stored its own before the waits' bits)
           if (cnt.status) a.carry[ci].status |= (int)cnt.status;
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.epoch_done + ci), "r"(epoch + 1) : "memory");
+          if (a.epoch_flags_host != nullptr) {         // last item of the epoch: its rows may leave for the host now
+            __threadfence();
+            if (atomicAdd(a.epoch_count + epoch, 1u) + 1u == (unsigned)a.M * (unsigned)a.S) {
+              __threadfence_system();
+              *reinterpret_cast<volatile int*>(a.epoch_flags_host + epoch) = 1;
+            }
+          }
         }
         return;
       }
@@ -1080,8 +1093,8 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
   size_t off_po, off_pid, off_bylevel, off_lvlstart, off_topo_end, off_order, off_area, off_lvl_items, off_lvl_order, off_oc,
-      off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket, off_progress, off_epoch_done, off_flux,
-      off_obs_log,
+      off_cost, off_hist, off_perm, off_plan, off_carry, off_carry_stats, off_ticket, off_progress, off_epoch_done,
+      off_epoch_count, off_flux, off_obs_log,
       off_obs_rank, off_sim_obs, total;
 };
 
@@ -1114,6 +1127,8 @@ WsLayout ws_layout(const SimplypDims& d, int n_edges, bool cal, bool ranks = fal
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
   L.off_epoch_done = o;
   if (d.n_sc > 1) o = align_up(o + sizeof(int) * (size_t)d.n_members * d.n_sc);
+  L.off_epoch_count = o;
+  if (d.n_sc > 1) o = align_up(o + sizeof(unsigned) * ((size_t)d.n_days / FORC_TILE + 2));
   L.off_flux = o;
   if (cal && d.n_sc > 1) o = align_up(o + sizeof(double) * 4 * (size_t)d.n_members * d.n_sc * d.n_days);
   L.off_obs_log = o;
@@ -1309,9 +1324,18 @@ __global__ void stiff_group_kernel(int S, int n_levels, int M, const int* by_lev
 
 // Shared launcher: one launch; the reach DAG is swept as a day-skewed wavefront inside the kernel.  Everything is
 // enqueued on `st`; nothing here waits for the device.
+// What a *_host entry point needs to stream finished epochs of a network launch to the caller (see KArgs): in, the
+// device pointer of its mapped flags and how many there are; out, the epochs of the launch (n_epochs <= 1: no sweep,
+// nothing is signalled).
+struct EpochStream {
+  int* flags_dev = nullptr;
+  int capacity = 0;
+  int n_epochs = 0, epoch_days = 0;
+};
+
 template <bool CAL>
 int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, const int32_t* po_host,
-                  const int32_t* pid_host, char* ws, cudaStream_t st) {
+                  const int32_t* pid_host, char* ws, cudaStream_t st, EpochStream* es = nullptr) {
   const int S = dims.n_sc;
   std::vector<int> lvl;
   const int nl = topology_levels(S, po_host, pid_host, lvl);
@@ -1403,6 +1427,12 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
     a.carry = reinterpret_cast<QuadCarry*>(ws + L.off_carry);
     a.carry_stats = reinterpret_cast<double*>(ws + L.off_carry_stats);
     grid *= a.n_epochs;
+    if (es != nullptr && es->flags_dev != nullptr && a.n_epochs <= es->capacity) {
+      a.epoch_count = reinterpret_cast<unsigned*>(ws + L.off_epoch_count);
+      a.epoch_flags_host = es->flags_dev;
+      es->n_epochs = a.n_epochs;
+      es->epoch_days = a.epoch_days;
+    }
   }
   // Networks get the build with the Rosenbrock path for stiff (main-stem) reaches.  Its 2-blocks-per-SM variant (226
   // registers) serves launches that the chains of the main stem bound; when the items of one epoch fill the machine
@@ -1444,7 +1474,11 @@ struct HostCache {
   void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // device-to-host copies of finished epochs, beside the integration
+  int* epoch_flags = nullptr;             // mapped pinned memory [EPOCH_FLAGS]: raised by the kernel, polled by the host
+  int* epoch_flags_dev = nullptr;
 };
+constexpr int EPOCH_FLAGS = 4096;
 HostCache g_cache[MAX_DEVICES];
 
 int cache_get(HostCache& c, int slot, size_t bytes, void** out) {
@@ -1464,6 +1498,11 @@ int cache_get(HostCache& c, int slot, size_t bytes, void** out) {
 int cache_select_device(int device, HostCache& c) {
   SP_CUDA(cudaSetDevice(device));
   if (!c.stream) SP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  if (!c.copy_stream) SP_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  if (!c.epoch_flags) {
+    SP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c.epoch_flags), sizeof(int) * EPOCH_FLAGS, cudaHostAllocMapped));
+    SP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c.epoch_flags_dev), c.epoch_flags, 0));
+  }
   return SIMPLYP_OK;
 }
 
@@ -1516,9 +1555,10 @@ int64_t simplyp_workspace_bytes(const SimplypDims* dims, int calibrate) {
   return (int64_t)ws_layout(*dims, dims->reserved[0], (calibrate & 1) != 0, (calibrate & 2) != 0).total;
 }
 
-int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
-                       const double* member_params, const double* sc_params, const int32_t* parent_offsets,
-                       const int32_t* parent_ids, double* out, int64_t* diag, void* workspace, void* stream) {
+static int run_device_impl(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                           const double* member_params, const double* sc_params, const int32_t* parent_offsets,
+                           const int32_t* parent_ids, double* out, int64_t* diag, void* workspace, void* stream,
+                           EpochStream* es) {
   int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
   if (rc) return rc;
   if (!out) return fail(SIMPLYP_EINVAL, "null output%s");
@@ -1528,7 +1568,14 @@ int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const
   a.out = out;
   a.diag = reinterpret_cast<long long*>(diag);
   return launch_levels<false>(*dims, *opt, a, parent_offsets, parent_ids, static_cast<char*>(workspace),
-                              static_cast<cudaStream_t>(stream));
+                              static_cast<cudaStream_t>(stream), es);
+}
+
+int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                       const double* member_params, const double* sc_params, const int32_t* parent_offsets,
+                       const int32_t* parent_ids, double* out, int64_t* diag, void* workspace, void* stream) {
+  return run_device_impl(dims, opt, forcing, member_params, sc_params, parent_offsets, parent_ids, out, diag, workspace,
+                         stream, nullptr);
 }
 
 int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
@@ -1622,9 +1669,39 @@ int simplyp_run_host(int device, const SimplypDims* dims, const SimplypOptions* 
   SP_CUDA(cudaMemcpyAsync(d_forc, forcing, b_forc, cudaMemcpyHostToDevice, st));
   SP_CUDA(cudaMemcpyAsync(d_mp, member_params, b_mp, cudaMemcpyHostToDevice, st));
   SP_CUDA(cudaMemcpyAsync(d_sc, sc_params, b_sc, cudaMemcpyHostToDevice, st));
-  rc = simplyp_run_device(dims, opt, (const double*)d_forc, (const double*)d_mp, (const double*)d_sc,
-                          parent_offsets, parent_ids, (double*)d_out, (int64_t*)d_diag, d_ws, st);
+  EpochStream es;
+  es.flags_dev = hc.epoch_flags_dev;
+  es.capacity = EPOCH_FLAGS;
+  memset(hc.epoch_flags, 0, sizeof(int) * EPOCH_FLAGS);       // (the previous call on this device has finished: see the lock)
+  rc = run_device_impl(dims, opt, (const double*)d_forc, (const double*)d_mp, (const double*)d_sc, parent_offsets,
+                       parent_ids, (double*)d_out, (int64_t*)d_diag, d_ws, st, &es);
   if (rc) return rc;
+  if (es.n_epochs > 1) {
+    // A network swept in epochs: the rows of epoch e (days [e E, (e+1) E) of every item: a strided 2-D block of the
+    // [M][S][D][25] array) are final once every item has finished it, and leave on the copy stream while the later
+    // epochs integrate.  The kernel raises one mapped flag per epoch; the last epoch is copied after the kernel.
+    const size_t row = sizeof(double) * SIMPLYP_NOUT, pitch = row * D;
+    int copied = 0;
+    volatile int* flags = hc.epoch_flags;
+    while (copied + 1 < es.n_epochs) {
+      if (!flags[copied]) {
+        if (cudaStreamQuery(st) != cudaErrorNotReady) break;   // finished (or failed): the rest is copied below
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+        continue;
+      }
+      const size_t d0 = (size_t)copied * es.epoch_days;
+      SP_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(out) + row * d0, pitch, reinterpret_cast<const char*>(d_out) + row * d0,
+                                pitch, row * es.epoch_days, M * S, cudaMemcpyDeviceToHost, hc.copy_stream));
+      ++copied;
+    }
+    SP_CUDA(cudaStreamSynchronize(st));
+    const size_t d0 = (size_t)copied * es.epoch_days;
+    SP_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(out) + row * d0, pitch, reinterpret_cast<const char*>(d_out) + row * d0,
+                              pitch, row * (D - d0), M * S, cudaMemcpyDeviceToHost, hc.copy_stream));
+    if (diag) SP_CUDA(cudaMemcpyAsync(diag, d_diag, b_diag, cudaMemcpyDeviceToHost, hc.copy_stream));
+    SP_CUDA(cudaStreamSynchronize(hc.copy_stream));
+    return SIMPLYP_OK;
+  }
   SP_CUDA(cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, st));
   if (diag) SP_CUDA(cudaMemcpyAsync(diag, d_diag, b_diag, cudaMemcpyDeviceToHost, st));
   SP_CUDA(cudaStreamSynchronize(st));
@@ -1715,7 +1792,7 @@ void simplyp_release_cache(void) {
   for (int d = 0; d < MAX_DEVICES; ++d) {
     HostCache& c = g_cache[d];
     std::lock_guard<std::mutex> guard(c.lock);
-    if (!c.stream && !c.buf[0]) continue;
+    if (!c.stream && !c.buf[0] && !c.epoch_flags) continue;
     if (d < n) cudaSetDevice(d);
     for (int i = 0; i < 8; ++i) {
       if (c.buf[i]) cudaFree(c.buf[i]);
@@ -1724,6 +1801,11 @@ void simplyp_release_cache(void) {
     }
     if (c.stream) cudaStreamDestroy(c.stream);
     c.stream = nullptr;
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    c.copy_stream = nullptr;
+    if (c.epoch_flags) cudaFreeHost(c.epoch_flags);
+    c.epoch_flags = nullptr;
+    c.epoch_flags_dev = nullptr;
   }
   if (prev >= 0) cudaSetDevice(prev);
   std::lock_guard<std::mutex> lock(g_topo_mutex);
