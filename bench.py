@@ -355,8 +355,30 @@ def run_ours(args):
         # the kernel writes this rank's statistics straight into its slot of the pre-allocated gather buffer
         gb = ens.GatherBuffers(M_total, (V, pk.NSTAT), eng.device)
         stats = gb.local
+        # N > 1: the all-gather is fused into the calibration kernel (peer stores into every rank's buffer + a flag
+        # exchange, ensemble.PeerGather) where CUDA IPC between the ranks works; SIMPLYP_GATHER=nccl keeps NCCL
+        pg = None
+        if world > 1 and os.environ.get("SIMPLYP_GATHER", "peer") != "nccl":
+            ok = torch.zeros(1, device=eng.device)
+            try:
+                pg = ens.PeerGather(M_total, (V, pk.NSTAT), eng.device)
+                ok += 1
+            except Exception as e:
+                sys.stderr.write("rank %d: peer gather unavailable (%r), using NCCL\n" % (rank, e))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1 and pg is not None:
+                pg.close()
+                pg = None
+        gather_mode = ("peer-memory stores fused into the calibration kernel + flag exchange" if pg is not None
+                       else ("NCCL all_gather_into_tensor, in place" if world > 1 else "none (one rank)"))
+        last = {}
 
         def step(mid=None):
+            if pg is not None:
+                last["g"], _ = eng.calibrate(d_forc, d_mem, d_sc, po, pid, d_obs, d_desc, opt, diag=diag, peer_gather=pg)
+                if mid is not None:
+                    mid.record()
+                return last["g"]
             eng.calibrate(d_forc, d_mem, d_sc, po, pid, d_obs, d_desc, opt, stats=stats, diag=diag)
             if mid is not None:
                 mid.record()               # this rank's own integration ends here; the all-gather waits for the slowest rank
@@ -426,7 +448,7 @@ def run_ours(args):
     kernel_ms = float(np.mean(step_ms))
     fp64_peak = _cabi.measure_fp64_peak(local_rank, 3) if rank == 0 else None
     if calibration:
-        stats_ref = stats.clone()
+        stats_ref = (last["g"][lo:hi] if pg is not None else stats).clone()
         alg_bytes = (d_forc.numel() + d_mem.numel() + d_sc.numel() + d_obs.numel()) * 8 + stats.numel() * 8 * 2
     else:
         alg_bytes = units_local * B_DAY + (d_forc.numel() + d_mem.numel() + d_sc.numel()) * 8
@@ -556,8 +578,10 @@ def run_ours(args):
                     "api": api, "members_per_gpu": M_e2e, "steps": e2e_reps, "matches_device_leg": same},
             "roofline": roofline,
             "clocks": clocks, "integrator_status_bits": status_any, "wall_s_timed_region": t_wall,
-            "ranks_own_ms_per_step": ranks_own_ms,
+            "ranks_own_ms_per_step": ranks_own_ms if not (calibration and pg is not None) else None,
         }
+        if calibration:
+            line["config"]["gather"] = gather_mode
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_legs(args, opt.rtol, opt.atol, D)

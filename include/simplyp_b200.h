@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SIMPLYP_ABI_VERSION 3
+#define SIMPLYP_ABI_VERSION 4
 
 /* error codes */
 #define SIMPLYP_OK          0
@@ -232,6 +232,45 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
                              const int32_t* parent_offsets, const int32_t* parent_ids,
                              const double* obs, const int32_t* obs_desc,
                              double* stats, int64_t* diag, void* workspace, void* stream);
+
+/* Calibration mode fused with the all-gather of the statistics over peer memory (one process per GPU, NVLink /
+ * NVSwitch): every rank integrates members [member_offset, member_offset + dims->n_members) of an ensemble of
+ * n_members_total and its kernel stores each finished member's statistics straight into EVERY rank's gather buffer
+ * (peer stores), so that the only thing left after the integration is a flag exchange: the rank raises `step` in
+ * every peer's flag array and waits until every peer has raised it in its own (one small kernel, enqueued on `stream`).
+ *   stats_bufs[r] : rank r's gather buffer [n_members_total][V][SIMPLYP_NSTAT] as mapped into THIS process
+ *                   (own: an ordinary device pointer; peers: simplyp_ipc_import of their simplyp_ipc_export handle)
+ *   flag_bufs[r]  : rank r's flags int32[SIMPLYP_MAX_RANKS], zero before the first call; flag_bufs[r][q] = last step
+ *                   rank q has finished
+ *   step          : strictly increasing from call to call, the same on all ranks.  A caller that reuses the buffers
+ *                   alternates between two sets (a fast rank writes step k+1 while a slow one still reads step k).
+ * The caller's `stats` argument is replaced by stats_bufs[rank] + member_offset rows.  SimplypOptions.rank_stats must
+ * be 0 (Spearman's r is filled by a later kernel).  After the flag kernel, diag status bit 8 (on member 0, series 0 of
+ * this rank) reports a peer that did not answer within ~2 s.  Replaces, on this path, torch.distributed's
+ * all_gather_into_tensor (the reference has no multi-process form: Development/2016/MCMC.ipynb:29-31,380 uses an
+ * IPython.parallel pool). */
+#define SIMPLYP_MAX_RANKS 8
+typedef struct {
+  int32_t  n_ranks, rank;
+  int64_t  member_offset, n_members_total;
+  int64_t  step;
+  double*  stats_bufs[SIMPLYP_MAX_RANKS];
+  int32_t* flag_bufs[SIMPLYP_MAX_RANKS];
+} SimplypPeerGather;
+
+int simplyp_calibrate_gather_device(const SimplypDims* dims, const SimplypOptions* opt,
+                                    const double* forcing, const double* member_params, const double* sc_params,
+                                    const int32_t* parent_offsets, const int32_t* parent_ids,
+                                    const double* obs, const int32_t* obs_desc,
+                                    const SimplypPeerGather* gather, int64_t* diag, void* workspace, void* stream);
+
+/* Peer-visible device memory for the buffers above: a zeroed cudaMalloc allocation of its own (an IPC handle maps a
+ * whole allocation), its 64-byte CUDA IPC handle, and the mapping of another process's handle into this one. */
+int simplyp_peer_alloc(int64_t bytes, void** dptr);
+int simplyp_peer_free(void* dptr);
+int simplyp_ipc_export(const void* dptr, unsigned char handle[64]);
+int simplyp_ipc_import(const unsigned char handle[64], void** dptr);
+int simplyp_ipc_close(void* dptr);
 
 /* sum_to_waterbody (model.py:851-900) on the raw output of simplyp_run_device, for every member and day:
  *   out[M][S][D][25], reaches[n_reaches] = run-order indices of the reaches with In_final_flux? == 1 (device),

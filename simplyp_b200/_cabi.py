@@ -23,7 +23,10 @@ EXPORTS = [
     "simplyp_run_device", "simplyp_calibrate_device", "simplyp_run_host", "simplyp_calibrate_host",
     "simplyp_release_cache", "simplyp_launch_count", "simplyp_measure_fp64_peak",
     "simplyp_measure_fp64_latency", "simplyp_sum_to_waterbody_device", "simplyp_thornthwaite_pet_device",
+    "simplyp_calibrate_gather_device", "simplyp_peer_alloc", "simplyp_peer_free", "simplyp_ipc_export",
+    "simplyp_ipc_import", "simplyp_ipc_close",
 ]
+MAX_RANKS = 8
 
 
 class SimplypDims(C.Structure):
@@ -37,6 +40,12 @@ class SimplypOptions(C.Structure):
                 ("dynamic_erodibility", C.c_int32), ("run_mode_cal", C.c_int32), ("sc_qr0", C.c_int32),
                 ("strict_quirks", C.c_int32), ("threads_per_block", C.c_int32), ("lanes_per_item", C.c_int32),
                 ("pilot_days", C.c_int32), ("rank_stats", C.c_int32), ("snow_on_device", C.c_int32), ("reserved", C.c_int32 * 1)]
+
+
+class SimplypPeerGather(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("member_offset", C.c_int64),
+                ("n_members_total", C.c_int64), ("step", C.c_int64), ("stats_bufs", C.c_void_p * MAX_RANKS),
+                ("flag_bufs", C.c_void_p * MAX_RANKS)]
 
 
 class SimplypError(RuntimeError):
@@ -89,7 +98,20 @@ def load():
     lib.simplyp_thornthwaite_pet_device.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_double, vp,
                                                     C.c_int32, vp]
     lib.simplyp_thornthwaite_pet_device.restype = C.c_int
-    if lib.simplyp_abi_version() != 3:
+    lib.simplyp_calibrate_gather_device.argtypes = [C.POINTER(SimplypDims), C.POINTER(SimplypOptions), vp, vp, vp, ip,
+                                                    ip, vp, vp, C.POINTER(SimplypPeerGather), vp, vp, vp]
+    lib.simplyp_calibrate_gather_device.restype = C.c_int
+    lib.simplyp_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+    lib.simplyp_peer_alloc.restype = C.c_int
+    lib.simplyp_peer_free.argtypes = [vp]
+    lib.simplyp_peer_free.restype = C.c_int
+    lib.simplyp_ipc_export.argtypes = [vp, C.c_char_p]
+    lib.simplyp_ipc_export.restype = C.c_int
+    lib.simplyp_ipc_import.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.simplyp_ipc_import.restype = C.c_int
+    lib.simplyp_ipc_close.argtypes = [vp]
+    lib.simplyp_ipc_close.restype = C.c_int
+    if lib.simplyp_abi_version() != 4:
         raise SimplypError("ABI version mismatch")
     _lib = lib
     return lib
@@ -232,6 +254,42 @@ def calibrate_device(dims, opt, forcing_ptr, member_ptr, sc_ptr, parent_offsets,
     po, pid = _topology_arrays(parent_offsets, parent_ids)
     _check(lib.simplyp_calibrate_device(C.byref(dims), C.byref(opt), forcing_ptr, member_ptr, sc_ptr, _iptr(po),
                                         _iptr(pid), obs_ptr, desc_ptr, stats_ptr, diag_ptr, ws_ptr, stream_ptr))
+
+
+def calibrate_gather_device(dims, opt, forcing_ptr, member_ptr, sc_ptr, parent_offsets, parent_ids, obs_ptr, desc_ptr,
+                            gather, diag_ptr, ws_ptr, stream_ptr):
+    """Calibration fused with the all-gather of the statistics over peer memory (``gather``: SimplypPeerGather)."""
+    lib = require_device()
+    po, pid = _topology_arrays(parent_offsets, parent_ids)
+    _check(lib.simplyp_calibrate_gather_device(C.byref(dims), C.byref(opt), forcing_ptr, member_ptr, sc_ptr, _iptr(po),
+                                               _iptr(pid), obs_ptr, desc_ptr, C.byref(gather), diag_ptr, ws_ptr,
+                                               stream_ptr))
+
+
+def peer_alloc(n_bytes):
+    p = C.c_void_p()
+    _check(require_device().simplyp_peer_alloc(int(n_bytes), C.byref(p)))
+    return int(p.value)
+
+
+def peer_free(ptr):
+    _check(load().simplyp_peer_free(C.c_void_p(ptr)))
+
+
+def ipc_export(ptr):
+    buf = C.create_string_buffer(64)
+    _check(load().simplyp_ipc_export(C.c_void_p(ptr), buf))
+    return bytes(buf.raw)
+
+
+def ipc_import(handle):
+    p = C.c_void_p()
+    _check(load().simplyp_ipc_import(C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(ptr):
+    _check(load().simplyp_ipc_close(C.c_void_p(ptr)))
 
 
 def sum_to_waterbody_device(dims, out_ptr, sc_ptr, member_ptr, reaches_ptr, n_reaches, wb_ptr, stream_ptr):

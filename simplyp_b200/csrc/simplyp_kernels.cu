@@ -105,6 +105,11 @@ struct KArgs {
   // last item to finish epoch e raises epoch_flags_host[e] (mapped pinned memory), which the host thread polls
   unsigned* epoch_count;        // [n_epochs] items that have finished the epoch, or null
   int* epoch_flags_host;        // [n_epochs] device pointer of the mapped flags, or null
+  // calibration fused with the all-gather of the statistics (simplyp_calibrate_gather_device): every rank's gather
+  // buffer as mapped into this process; finalise() stores a member's statistics into all of them
+  double* peer_stats[SIMPLYP_MAX_RANKS];
+  int n_peers, my_rank;         // n_peers = 0: no gather
+  long long member_offset;      // this rank's first member in the buffers
   int* plan;                    // placement of a cost-ordered ensemble on the SMs (PLAN_* below), or null
   PlanShape shape;              // valid when plan != nullptr
 };
@@ -446,6 +451,14 @@ struct CalIO : IOBase<ROUTED> {
       rs[SIMPLYP_ST_SSE] = sse;
       rs[SIMPLYP_ST_SPEARMAN] = NAN;            // filled by spearman_kernel when rank statistics are on
       rs[SIMPLYP_ST_RESERVED] = 0.0;
+      // fused all-gather: the same ten numbers into the other ranks' buffers (peer stores over NVLink; `rs` is this
+      // rank's own buffer).  They are complete for the peers once this rank's flag kernel has run.
+      for (int r = 0; r < a.n_peers; ++r) {
+        if (r == a.my_rank) continue;
+        double* dst = a.peer_stats[r] + ((size_t)(a.member_offset + m) * a.V + v) * SIMPLYP_NSTAT;
+#pragma unroll
+        for (int i = 0; i < SIMPLYP_NSTAT; ++i) dst[i] = rs[i];
+      }
     }
   }
 };
@@ -1071,6 +1084,32 @@ __global__ void fp64_latency_kernel(double* sink, long long* cycles, int iters, 
   if (x == 123.456) sink[0] = x;
 }
 
+// ------------------------------------------------------------------------------------------ fused all-gather: flags
+// After the integration kernel of a rank (same stream): raise `step` in every peer's flag array, then wait until every
+// peer has raised it here.  The integration kernel has completed, so its peer stores are performed; the system-scope
+// fence + release order them before the flag for the peer that acquires it.  One thread per peer; a peer that does
+// not answer within ~2 s (globaltimer) sets status bit 8 instead of hanging the device.
+struct PeerFlags { int* bufs[SIMPLYP_MAX_RANKS]; };
+__global__ void peer_flag_kernel(PeerFlags f, int n, int rank, int step, long long* status_word) {
+  const int p = threadIdx.x;
+  if (p >= n || p == rank) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f.bufs[p] + rank), "r"(step) : "memory");
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f.bufs[rank] + p) : "memory");
+    if (v - step >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      if (status_word) atomicOr(reinterpret_cast<unsigned long long*>(status_word), 8ull);
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 int topology_levels(int S, const int32_t* po, const int32_t* pid, std::vector<int>& lvl) {
   lvl.assign(S, 0);
@@ -1578,11 +1617,11 @@ int simplyp_run_device(const SimplypDims* dims, const SimplypOptions* opt, const
                          stream, nullptr);
 }
 
-int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
-                             const double* member_params, const double* sc_params,
-                             const int32_t* parent_offsets, const int32_t* parent_ids, const double* obs,
-                             const int32_t* obs_desc, double* stats, int64_t* diag, void* workspace,
-                             void* stream) {
+static int calibrate_device_impl(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                                 const double* member_params, const double* sc_params,
+                                 const int32_t* parent_offsets, const int32_t* parent_ids, const double* obs,
+                                 const int32_t* obs_desc, double* stats, int64_t* diag, void* workspace,
+                                 void* stream, const SimplypPeerGather* pg) {
   int rc = check_common(dims, opt, forcing, member_params, sc_params, parent_offsets);
   if (rc) return rc;
   if (dims->n_obs_series < 0 || (dims->n_obs_series > 0 && (!obs || !obs_desc || !stats)))
@@ -1599,6 +1638,12 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
   a.obs = obs;
   a.obs_desc = obs_desc;
   a.stats = stats;
+  if (pg != nullptr) {
+    a.n_peers = pg->n_ranks;
+    a.my_rank = pg->rank;
+    a.member_offset = pg->member_offset;
+    for (int r = 0; r < pg->n_ranks; ++r) a.peer_stats[r] = pg->stats_bufs[r];
+  }
   a.obs_const = reinterpret_cast<const double*>(ws + L.off_oc);
   double* obs_rank = reinterpret_cast<double*>(ws + L.off_obs_rank);
   if (V > 0) {
@@ -1639,6 +1684,74 @@ int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt,
     g_launches.fetch_add(1);
     SP_CUDA(cudaGetLastError());
   }
+  if (pg != nullptr && pg->n_ranks > 1) {
+    PeerFlags f;
+    for (int r = 0; r < SIMPLYP_MAX_RANKS; ++r) f.bufs[r] = r < pg->n_ranks ? pg->flag_bufs[r] : nullptr;
+    long long* status_word = diag ? reinterpret_cast<long long*>(diag) + SIMPLYP_DG_STATUS : nullptr;
+    peer_flag_kernel<<<1, 32, 0, st>>>(f, pg->n_ranks, pg->rank, (int)pg->step, status_word);
+    g_launches.fetch_add(1);
+    SP_CUDA(cudaGetLastError());
+  }
+  return SIMPLYP_OK;
+}
+
+int simplyp_calibrate_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                             const double* member_params, const double* sc_params,
+                             const int32_t* parent_offsets, const int32_t* parent_ids, const double* obs,
+                             const int32_t* obs_desc, double* stats, int64_t* diag, void* workspace,
+                             void* stream) {
+  return calibrate_device_impl(dims, opt, forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc,
+                               stats, diag, workspace, stream, nullptr);
+}
+
+int simplyp_calibrate_gather_device(const SimplypDims* dims, const SimplypOptions* opt, const double* forcing,
+                                    const double* member_params, const double* sc_params,
+                                    const int32_t* parent_offsets, const int32_t* parent_ids, const double* obs,
+                                    const int32_t* obs_desc, const SimplypPeerGather* gather, int64_t* diag,
+                                    void* workspace, void* stream) {
+  if (!gather || !dims) return fail(SIMPLYP_EINVAL, "null gather descriptor%s");
+  if (gather->n_ranks < 1 || gather->n_ranks > SIMPLYP_MAX_RANKS || gather->rank < 0 || gather->rank >= gather->n_ranks)
+    return fail(SIMPLYP_EINVAL, "gather: 1..SIMPLYP_MAX_RANKS ranks, rank inside%s");
+  if (gather->member_offset < 0 || gather->member_offset + dims->n_members > gather->n_members_total)
+    return fail(SIMPLYP_EINVAL, "gather: this rank's members must lie inside the ensemble%s");
+  if (opt && opt->rank_stats) return fail(SIMPLYP_EINVAL, "gather: rank statistics are filled by a later kernel, use the plain entry point%s");
+  for (int r = 0; r < gather->n_ranks; ++r)
+    if (!gather->stats_bufs[r] || !gather->flag_bufs[r]) return fail(SIMPLYP_EINVAL, "gather: null peer buffer%s");
+  double* stats = gather->stats_bufs[gather->rank] +
+                  (size_t)gather->member_offset * (dims->n_obs_series > 0 ? dims->n_obs_series : 0) * SIMPLYP_NSTAT;
+  return calibrate_device_impl(dims, opt, forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc,
+                               stats, diag, workspace, stream, gather);
+}
+
+int simplyp_peer_alloc(int64_t bytes, void** dptr) {
+  if (!dptr || bytes <= 0) return fail(SIMPLYP_EINVAL, "peer_alloc: bad argument%s");
+  if (simplyp_device_count() <= 0) return fail(SIMPLYP_ENODEVICE, "no CUDA device%s");
+  SP_CUDA(cudaMalloc(dptr, (size_t)bytes));
+  SP_CUDA(cudaMemset(*dptr, 0, (size_t)bytes));
+  SP_CUDA(cudaDeviceSynchronize());
+  return SIMPLYP_OK;
+}
+int simplyp_peer_free(void* dptr) {
+  if (dptr) SP_CUDA(cudaFree(dptr));
+  return SIMPLYP_OK;
+}
+int simplyp_ipc_export(const void* dptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!dptr || !handle) return fail(SIMPLYP_EINVAL, "ipc_export: null argument%s");
+  cudaIpcMemHandle_t h;
+  SP_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+  memcpy(handle, &h, 64);
+  return SIMPLYP_OK;
+}
+int simplyp_ipc_import(const unsigned char handle[64], void** dptr) {
+  if (!dptr || !handle) return fail(SIMPLYP_EINVAL, "ipc_import: null argument%s");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  SP_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SIMPLYP_OK;
+}
+int simplyp_ipc_close(void* dptr) {
+  if (dptr) SP_CUDA(cudaIpcCloseMemHandle(dptr));
   return SIMPLYP_OK;
 }
 

@@ -81,8 +81,12 @@ class Engine:
 
     # ------------------------------------------------------------------ fused statistics
     def calibrate(self, forcing, member_params, sc_params, parent_offsets, parent_ids, obs, obs_desc, opt,
-                  stats=None, diag=None, max_workspace_bytes=None):
+                  stats=None, diag=None, max_workspace_bytes=None, peer_gather=None):
         """Returns (stats [M][V][10], diag [M][S][4]); asynchronous on the current stream.
+
+        With ``peer_gather`` (an :class:`ensemble.PeerGather`; the members given here are this rank's shard) the
+        statistics of ALL ranks come back, [M_total][V][10]: the kernel stores them into every rank's buffer and a flag
+        exchange ends the call on the stream — no collective follows.
 
         The workspace grows with the members: M*S*D*32 bytes of flux exchange for networks (S > 1) and M*V*D*8
         bytes of simulated values with ``opt.rank_stats``; members are processed in chunks that keep it under
@@ -92,7 +96,7 @@ class Engine:
         D, M, Msc, S, sc_params = self._shapes(forcing, member_params, sc_params)
         V = obs.shape[0]
         n_edges = int(parent_offsets[-1])
-        if stats is None:
+        if stats is None and peer_gather is None:
             stats = torch.empty((M, V, pk.NSTAT), dtype=torch.float64, device=self.device)
         if diag is None:
             diag = torch.zeros((M, S, pk.NDIAG), dtype=torch.int64, device=self.device)
@@ -101,6 +105,18 @@ class Engine:
         if per_member > 0:
             budget = max_workspace_bytes if max_workspace_bytes is not None else self.free_bytes() // 2
             chunk = max(1, min(M, int(budget // per_member)))
+        if peer_gather is not None:
+            if chunk < M or opt.rank_stats or M != peer_gather.hi - peer_gather.lo:
+                raise _cabi.SimplypError("peer_gather: one launch of this rank's whole shard, without rank statistics")
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                dims = _cabi.make_dims(M, S, D, 1 if Msc == 1 else M, V, n_edges)
+                ws = self._workspace(_cabi.workspace_bytes(dims, True, False))
+                desc, gathered = peer_gather.descriptor()
+                _cabi.calibrate_gather_device(dims, opt, forcing.data_ptr(), member_params.data_ptr(),
+                                              sc_params.data_ptr(), parent_offsets, parent_ids, obs.data_ptr(),
+                                              obs_desc.data_ptr(), desc, diag.data_ptr(), ws.data_ptr(), stream)
+            return gathered, diag
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             for m0 in range(0, M, chunk):

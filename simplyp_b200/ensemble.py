@@ -134,6 +134,88 @@ class GatherBuffers:
         return self.compact
 
 
+class PeerGather:
+    """The all-gather of the per-member fit statistics FUSED into the calibration kernel (one process per GPU of one
+    NVLink / NVSwitch box): every rank maps every other rank's gather buffer (CUDA IPC) and its kernel stores each
+    finished member's statistics straight into all of them; after the integration only a flag exchange is left
+    (``simplyp_calibrate_gather_device``, include/simplyp_b200.h).  Replaces ``GatherBuffers`` + NCCL on this path;
+    ``torch.distributed`` is used once, to exchange the IPC handles.
+
+    Two buffer sets alternate from call to call (a fast rank may write step k+1 while a slow one still reads step k):
+    the tensor :meth:`Engine.calibrate` returns is valid until the call after the next one.
+    Raises ``SimplypError`` where CUDA IPC or peer access is not available — fall back to ``GatherBuffers``.
+    """
+
+    def __init__(self, n_members, tail_shape, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _cabi
+
+        self.group = group
+        self.n_members = int(n_members)
+        self.tail = tuple(int(x) for x in tail_shape)
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _cabi.MAX_RANKS:
+            raise _cabi.SimplypError("PeerGather: at most %d ranks" % _cabi.MAX_RANKS)
+        self.lo, self.hi = shard_bounds(self.n_members, self.world, self.rank)
+        self.buf_bytes = (8 * self.n_members * int(np.prod(self.tail)) + 255) // 256 * 256
+        self.flag_bytes = 256
+        self.step = 0
+        self._peers = []
+        with torch.cuda.device(self.device):
+            self.base = _cabi.peer_alloc(self.flag_bytes + 2 * self.buf_bytes)
+            handle = _cabi.ipc_export(self.base)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            self.bases = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.bases.append(self.base)
+                else:
+                    ptr = _cabi.ipc_import(h)
+                    self._peers.append(ptr)
+                    self.bases.append(ptr)
+        self._views = [self._tensor(self.base + self.flag_bytes + k * self.buf_bytes) for k in range(2)]
+
+    def _tensor(self, ptr):
+        import torch
+
+        shape = (self.n_members,) + self.tail
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+        return torch.as_tensor(_Mem(), device=self.device)
+
+    def descriptor(self):
+        """SimplypPeerGather of the NEXT call (advances the step) and the tensor its result will be in."""
+        from . import _cabi
+
+        self.step += 1
+        k = self.step % 2
+        g = _cabi.SimplypPeerGather()
+        g.n_ranks, g.rank = self.world, self.rank
+        g.member_offset, g.n_members_total, g.step = self.lo, self.n_members, self.step
+        for r in range(self.world):
+            g.stats_bufs[r] = self.bases[r] + self.flag_bytes + k * self.buf_bytes
+            g.flag_bufs[r] = self.bases[r]
+        return g, self._views[k]
+
+    def close(self):
+        from . import _cabi
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        for ptr in self._peers:
+            _cabi.ipc_close(ptr)
+        self._peers = []
+        if self.base:
+            _cabi.peer_free(self.base)
+            self.base = 0
+
+
 _gather_cache = {}
 
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_cabi.EXPORTS) == declared
     lib2 = _cabi.load()
-    assert lib2.simplyp_abi_version() == 3
+    assert lib2.simplyp_abi_version() == 4
     assert b"sm_100a" in lib2.simplyp_version()
 
 

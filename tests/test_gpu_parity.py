@@ -234,6 +234,50 @@ def test_epoch_sweep_is_invisible_in_the_results(cabi, monkeypatch):
     assert res["0"][1][..., 0].min() > 700 * 3
 
 
+def test_fused_gather_entry_point_on_one_rank(cabi):
+    """simplyp_calibrate_gather_device (the calibration kernel that stores every member's statistics into all ranks'
+    gather buffers over peer memory) with ONE rank: a peer-visible allocation, its IPC handle, three passes through the
+    two alternating buffer sets, and statistics bit-identical to the plain entry point.  With N > 1 ranks the path is
+    checked against NCCL under torchrun (scripts/check_peer_gather.py: bitwise on 2 and 8 GPUs)."""
+    import torch
+    import torch.distributed as dist
+    from simplyp_b200 import ensemble as ens, model as spm, packing as pk, tarland
+    from simplyp_b200.engine import Engine
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+    try:
+        p_SU, dyn, p, p_LU, p_SC, p_struc, met, obs = tarland.load("2004-01-01", "2004-06-30", dynamic="y")
+        topo = pk.build_topology(p_struc, p["SC_list"])
+        opt = spm.make_options(p_SU, p, dyn, topo)
+        samples = ens.latin_hypercube(700, seed=13)
+        member, sc = ens.pack_members(pk.member_vector(p, p_LU), pk.sc_matrix(p_SC, topo.sc_ids), samples)
+        obs_m, desc, labels = pk.obs_arrays(obs, topo, met.index, ("Q", "TDP"))
+        eng = Engine(0)
+        args = (eng.to_device(pk.forcing_matrix(met)), eng.to_device(member), eng.to_device(sc), topo.parent_offsets,
+                topo.parent_ids, eng.to_device(obs_m), eng.to_device(desc), opt)
+        want, dg0 = eng.calibrate(*args)
+        pg = ens.PeerGather(700, (obs_m.shape[0], pk.NSTAT), eng.device)
+        assert len(cabi.ipc_export(pg.base)) == 64
+        try:
+            for _ in range(3):
+                got, dg = eng.calibrate(*args, peer_gather=pg)
+                torch.cuda.synchronize()
+                assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+                assert torch.equal(dg, dg0) and int(dg[..., 3].max().item()) == 0
+            with pytest.raises(cabi.SimplypError):
+                opt.rank_stats = 1
+                eng.calibrate(*args, peer_gather=pg)
+        finally:
+            opt.rank_stats = 0
+            pg.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_long_record_wraps_the_forcing_ring(cabi):
     """1,300 days = 11 forcing tiles through the 4-slot TMA ring (slots are re-armed and refilled), with
     members of very different speed in one block; member 0 is checked against the oracle over the whole window."""
