@@ -359,16 +359,11 @@ def run_ours(args):
         # exchange, ensemble.PeerGather) where CUDA IPC between the ranks works; SIMPLYP_GATHER=nccl keeps NCCL
         pg = None
         if world > 1 and os.environ.get("SIMPLYP_GATHER", "peer") != "nccl":
-            ok = torch.zeros(1, device=eng.device)
-            try:
+            try:           # (collective inside: succeeds or fails on all ranks together)
                 pg = ens.PeerGather(M_total, (V, pk.NSTAT), eng.device)
-                ok += 1
             except Exception as e:
-                sys.stderr.write("rank %d: peer gather unavailable (%r), using NCCL\n" % (rank, e))
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() < 1 and pg is not None:
-                pg.close()
                 pg = None
+                sys.stderr.write("rank %d: peer gather unavailable (%r), using NCCL\n" % (rank, e))
         gather_mode = ("peer-memory stores fused into the calibration kernel + flag exchange" if pg is not None
                        else ("NCCL all_gather_into_tensor, in place" if world > 1 else "none (one rank)"))
         last = {}
@@ -589,6 +584,8 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
+    if calibration and pg is not None:
+        pg.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -164,19 +164,36 @@ class PeerGather:
         self.flag_bytes = 256
         self.step = 0
         self._peers = []
+        # Every rank takes part in the exchange whatever happened locally (a rank that could not allocate or export
+        # sends None), so that a failure is seen by all ranks together and nobody waits in a collective alone.
+        self.base, handle, err = 0, None, None
         with torch.cuda.device(self.device):
-            self.base = _cabi.peer_alloc(self.flag_bytes + 2 * self.buf_bytes)
-            handle = _cabi.ipc_export(self.base)
+            try:
+                self.base = _cabi.peer_alloc(self.flag_bytes + 2 * self.buf_bytes)
+                handle = _cabi.ipc_export(self.base)
+            except _cabi.SimplypError as e:
+                err = e
             handles = [None] * self.world
             dist.all_gather_object(handles, handle, group=group)
             self.bases = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.bases.append(self.base)
-                else:
-                    ptr = _cabi.ipc_import(h)
-                    self._peers.append(ptr)
-                    self.bases.append(ptr)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            self.bases.append(self.base)
+                        else:
+                            ptr = _cabi.ipc_import(h)
+                            self._peers.append(ptr)
+                            self.bases.append(ptr)
+                except _cabi.SimplypError as e:
+                    err = e
+            elif err is None:
+                err = _cabi.SimplypError("PeerGather: a peer could not export its buffer")
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                self.close()
+                raise err if err is not None else _cabi.SimplypError("PeerGather: a peer could not map the buffers")
         self._views = [self._tensor(self.base + self.flag_bytes + k * self.buf_bytes) for k in range(2)]
 
     def _tensor(self, ptr):
@@ -208,12 +225,17 @@ class PeerGather:
         import torch
 
         torch.cuda.synchronize(self.device)
-        for ptr in self._peers:
-            _cabi.ipc_close(ptr)
-        self._peers = []
-        if self.base:
-            _cabi.peer_free(self.base)
-            self.base = 0
+        with torch.cuda.device(self.device):
+            for ptr in self._peers:
+                _cabi.ipc_close(ptr)
+            self._peers = []
+            # (an exported allocation must outlive its mappings in the other processes: every rank calls close())
+            import torch.distributed as dist
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)
+            if self.base:
+                _cabi.peer_free(self.base)
+                self.base = 0
 
 
 _gather_cache = {}
