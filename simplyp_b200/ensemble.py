@@ -167,33 +167,45 @@ class PeerGather:
         # Every rank takes part in the exchange whatever happened locally (a rank that could not allocate or export
         # sends None), so that a failure is seen by all ranks together and nobody waits in a collective alone.
         self.base, handle, err = 0, None, None
-        with torch.cuda.device(self.device):
-            try:
+        self.bases = []
+
+        def local_export():
+            with torch.cuda.device(self.device):
                 self.base = _cabi.peer_alloc(self.flag_bytes + 2 * self.buf_bytes)
-                handle = _cabi.ipc_export(self.base)
-            except _cabi.SimplypError as e:
+                return _cabi.ipc_export(self.base)
+
+        def local_import(handles):
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.bases.append(self.base)
+                    else:
+                        ptr = _cabi.ipc_import(h)
+                        self._peers.append(ptr)
+                        self.bases.append(ptr)
+
+        try:
+            handle = local_export()
+        except Exception as e:          # no device, no memory, IPC not permitted ...
+            err = e
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                local_import(handles)
+            except Exception as e:
                 err = e
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle, group=group)
-            self.bases = []
-            if err is None and all(h is not None for h in handles):
-                try:
-                    for r, h in enumerate(handles):
-                        if r == self.rank:
-                            self.bases.append(self.base)
-                        else:
-                            ptr = _cabi.ipc_import(h)
-                            self._peers.append(ptr)
-                            self.bases.append(ptr)
-                except _cabi.SimplypError as e:
-                    err = e
-            elif err is None:
-                err = _cabi.SimplypError("PeerGather: a peer could not export its buffer")
-            oks = [None] * self.world
-            dist.all_gather_object(oks, err is None, group=group)
-            if not all(oks):
+        elif err is None:
+            err = _cabi.SimplypError("PeerGather: a peer could not export its buffer")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            try:
                 self.close()
-                raise err if err is not None else _cabi.SimplypError("PeerGather: a peer could not map the buffers")
+            except Exception:
+                pass
+            msg = "PeerGather unavailable: %r" % (err,) if err is not None else "PeerGather: a peer could not map the buffers"
+            raise _cabi.SimplypError(msg)
         self._views = [self._tensor(self.base + self.flag_bytes + k * self.buf_bytes) for k in range(2)]
 
     def _tensor(self, ptr):
@@ -224,18 +236,21 @@ class PeerGather:
         from . import _cabi
         import torch
 
-        torch.cuda.synchronize(self.device)
-        with torch.cuda.device(self.device):
-            for ptr in self._peers:
-                _cabi.ipc_close(ptr)
-            self._peers = []
-            # (an exported allocation must outlive its mappings in the other processes: every rank calls close())
-            import torch.distributed as dist
-            if self.world > 1 and dist.is_initialized():
-                dist.barrier(group=self.group)
-            if self.base:
+        import torch.distributed as dist
+
+        if self._peers or self.base:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                for ptr in self._peers:
+                    _cabi.ipc_close(ptr)
+        self._peers = []
+        # (an exported allocation must outlive its mappings in the other processes: every rank calls close())
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        if self.base:
+            with torch.cuda.device(self.device):
                 _cabi.peer_free(self.base)
-                self.base = 0
+            self.base = 0
 
 
 _gather_cache = {}

@@ -342,6 +342,16 @@ for M2 in (11, 12):
         out = gb.gather()
         assert torch.equal(out, full2 + rep), (M2, rep)
     assert (out.data_ptr() == gb.buffer.data_ptr()) == (M2 == 12)
+# the fused gather (peer memory) needs CUDA: without a device its constructor fails — on BOTH ranks together, after
+# both have taken part in its handle exchange (nobody is left waiting in a collective), and there is no CPU fallback
+from simplyp_b200 import _cabi
+if _cabi.load().simplyp_device_count() <= 0:
+    try:
+        ens.PeerGather(12, (V, 10), "cuda:0")
+        raise AssertionError("PeerGather must not work without a CUDA device")
+    except _cabi.SimplypError:
+        pass
+    dist.barrier()
 dist.destroy_process_group()
 print("ok", dist.get_rank() if dist.is_initialized() else "")
 ''' % ROOT
