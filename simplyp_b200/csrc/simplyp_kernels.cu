@@ -1458,6 +1458,14 @@ int launch_levels(const SimplypDims& dims, const SimplypOptions& opt, KArgs a, c
   // 8 members 2565 / 2788 / 2550 / 2411 / 2348 ms, at 1 member 1339 / 1297 / 1244 / 1253 / 1279.
   int epoch_days = (4 * nl + FORC_TILE - 1) / FORC_TILE * FORC_TILE;
   if (epoch_days < 2 * FORC_TILE) epoch_days = 2 * FORC_TILE;
+  {
+    // a launch of at most one block per SM has no bulk phase to overlap with, and its chain warps have their SMs to
+    // themselves: swept in epochs they would only get neighbours (config 3 at 1 / 8 members, 15 / 72 blocks: 549 / 548
+    // ms in one piece, 590 / 573 in epochs; config 5 at 1 member, 227 blocks, still gains: 1394 -> 1307 ms)
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (grid <= (long long)n_sm) epoch_days = 0;
+  }
   if (const char* e = getenv("SIMPLYP_EPOCH_DAYS")) epoch_days = atoi(e) / FORC_TILE * FORC_TILE;   // 0: off (A/B runs)
   if (epoch_days > 0 && dims.n_days > epoch_days && grid * ((dims.n_days + epoch_days - 1) / epoch_days) < (1ll << 30)) {
     a.epoch_days = epoch_days;

@@ -204,8 +204,8 @@ def test_network_ensemble_lanes_share_a_warp(cabi):
 def test_epoch_sweep_is_invisible_in_the_results(cabi, monkeypatch):
     """Networks are swept in epochs (units of >= 256 days x a block of items, epoch-major, the midnight state of every item
     handed over through the workspace) so that the main-stem chains of one epoch run beside the headwaters of the next.
-    The hand-over is exact: 64 reaches x 3 members x 700 days in epochs of 128 days (6 epochs), 256 days (the default, 3)
-    and in one piece give the same bits — full output, diagnostics, and the fused statistics of a calibration run."""
+    The hand-over is exact: 64 reaches x 3 members x 700 days in epochs of 128 days (6 epochs), of 256 days (3) and in
+    one piece (also the default of a launch this small: all its blocks are resident at once) give the same bits — full output, diagnostics, and the fused statistics of a calibration run."""
     from simplyp_b200 import ensemble as ens, model as spm, packing as pk, synthetic, tarland
     p_SU, dyn, p, p_LU, p_SC0, p_struc0, met, obs = tarland.load("2003-06-01", "2005-04-30", dynamic="y")
     assert len(met) == 700
@@ -219,7 +219,7 @@ def test_epoch_sweep_is_invisible_in_the_results(cabi, monkeypatch):
     outlet = topo.sc_ids[-1]
     obs_m, desc, labels = pk.obs_arrays({outlet: obs[1]}, topo, met.index, ("Q", "TDP"))
     res = {}
-    for days in ("0", "128", None):
+    for days in ("0", "128", "256", None):
         if days is None:
             monkeypatch.delenv("SIMPLYP_EPOCH_DAYS", raising=False)
         else:
@@ -228,7 +228,7 @@ def test_epoch_sweep_is_invisible_in_the_results(cabi, monkeypatch):
         st, dgc = cabi.calibrate_host(forcing, member, sc, topo.parent_offsets, topo.parent_ids, obs_m, desc, opt)
         assert not np.any(dg[..., 3]) and not np.any(dgc[..., 3]) and np.all(np.isfinite(out))
         res[days] = (out, dg, st, dgc)
-    for days in ("128", None):
+    for days in ("128", "256", None):
         for a, b in zip(res["0"], res[days]):
             assert np.array_equal(a, b, equal_nan=True), days
     assert res["0"][1][..., 0].min() > 700 * 3
