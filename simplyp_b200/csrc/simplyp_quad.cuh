@@ -68,6 +68,9 @@
 #ifndef SP_H0_STIFF_C
 #define SP_H0_STIFF_C 0.15    // first step of a Rosenbrock day <= this / rate: the boundary layer the midnight jump of the
 #endif                        // forcing excites is ~1/rate wide (saves the 5-6 rejections that found this step size)
+// Analysis knobs of the explicit pair's error norm (scripts/errnorm_exp.py, errnorm_validate.py); at 1.0 — the product's
+// setting: lower weights cost more accuracy on the light members than they save attempts, DESIGN.md section 4 — the
+// multiplications fold away.
 #ifndef SP_W_B
 #define SP_W_B 1.0     // weight of the slot-B (in-stream masses, Vr) terms of the error norm
 #define SP_W_ACC 1.0   // weight of the daily accumulators
